@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of SURF detect+describe on synthetic 1080p frames (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (integral -> Hessian -> NMS+refine -> descriptors) over one batch
+of B distinct synthetic frames per GPU. Workload = BASELINE.json configs[1] (1920x1080 `synth_v1`
+frames, 5 octaves x 5 layers -- the reference's max_scale for lobe 3, SURVEY.md 2.4-1 -- thresh 4,
+upright 64-d descriptors), batched as configs[3] shards it: frames are independent, ranks own
+contiguous shards, no data-path collective (scaling "weak": B frames per GPU).
+
+  value  whole-job frames/s with the batch resident in HBM, CUDA events on the launching stream,
+         barrier + synchronize on both sides, max over ranks.
+  e2e    the same through the host-buffer C-ABI call (sb_detect_batch_host): H2D of the frames and
+         D2H of counts + keypoints + descriptors inside the timed region.
+  roofline / cpu_baseline: see DESIGN.md "Measurement".
+--impl reference times the reference's own implementation (oracle/_ref, the unmodified CUDA sources
+built for sm_100a, through Surfor::detectAndCompute as main.cpp:239-245 calls it); if that library is
+absent, the CPU port under oracle/ on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1920, 1080
+NOCT, THRESH = 5, 4.0
+MAX_PTS = 16384
+POOL = 16  # distinct generated frames; the batch is filled with horizontally rolled copies
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def make_frames(n, sb):
+    pool = [sb.synth_frame(W, H, 1 + i) for i in range(min(POOL, n))]
+    out = np.empty((n, H, W), np.uint8)
+    for f in range(n):
+        out[f] = np.roll(pool[f % len(pool)], 37 * (f // len(pool)), axis=1)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(info, noct, n_kp, nfeat):
+    """compulsory traffic of a staged pipeline, per frame (unpadded sizes)."""
+    b_img = W * H
+    b_int = 4 * (W + 1) * (H + 1)
+    b_resp = 4 * info.max_scale * sum(info.sw[o] * info.sh[o] for o in range(noct))
+    b_kp, b_desc = 48 * n_kp, 4 * nfeat * n_kp
+    return {"integral": b_img + b_int, "hessian": b_int + b_resp, "nms": b_resp + b_kp,
+            "describe": b_int + b_kp + b_desc}
+
+
+def run_ours(args, rank, world, local_rank, dist):
+    import torch
+    import cuda_surf_b200 as sb
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+    det = sb.Surfor()
+    det.init(NOCT, THRESH, False, 9, 2, True, False, 4, W, H, max_pts=MAX_PTS, batch=B, device=local_rank)
+    nf = det.nfeatures
+    # this rank's shard of the global batch (contiguous; frames independent)
+    lo, hi = sb.shard_range(B * world, world, rank)
+    frames = make_frames(B, sb) if world == 1 else np.roll(make_frames(B, sb), 11 * rank, axis=2)
+    pitch = sb.iAlignUp(W, 128)
+    h_pad = np.zeros((B, H, pitch), np.uint8)
+    h_pad[:, :, :W] = frames
+    d_imgs = torch.from_numpy(h_pad).to(dev)
+    pts = torch.zeros((B, MAX_PTS * 48), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    desc = torch.zeros((B, MAX_PTS, nf), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        det.detect_batch(d_imgs, pitch, pts, cnt, desc)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        det.detect_batch(d_imgs, pitch, pts, cnt, desc)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = cnt.cpu().numpy()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = B * world * args.steps / (ms_max / 1e3)
+
+    # ---- per-stage times (CUDA events at the stage boundaries, same stream) -> roofline of the top kernel
+    stage = np.zeros(4)
+    for _ in range(args.steps):
+        stage += np.array(det.detect_batch_profile(d_imgs, pitch, pts, cnt, desc))
+    stage /= args.steps
+    names = ["integral", "hessian", "nms", "describe"]
+    kp_mean = float(counts.mean())
+    ab = algorithmic_bytes(det.info, NOCT, kp_mean, nf)
+    peak, peak_kind = peaks()
+    top = int(np.argmax(stage))
+    ach = ab[names[top]] * B / (stage[top] / 1e3) / 1e9
+    per_stage = {n: {"ms": float(stage[i]), "gbs": ab[n] * B / (stage[i] / 1e3) / 1e9,
+                     "frac": ab[n] * B / (stage[i] / 1e3) / 1e9 / peak} for i, n in enumerate(names)}
+    roofline = {"bound": "hbm", "kernel": names[top], "achieved": ach, "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "stages": per_stage,
+                "pipeline_frac": sum(ab.values()) * B / (float(stage.sum()) / 1e3) / 1e9 / peak}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host memory both ways)
+    h_frames = torch.from_numpy(frames).pin_memory()
+    h_pts = torch.zeros((B, MAX_PTS * 48), dtype=torch.uint8).pin_memory()
+    h_cnt = torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_desc = torch.zeros((B, MAX_PTS, nf), dtype=torch.float32).pin_memory()
+    for _ in range(max(1, args.warmup // 2)):
+        det.detect_batch_host(h_frames, h_pts, h_cnt, h_desc)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        det.detect_batch_host(h_frames, h_pts, h_cnt, h_desc)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    te = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = B * world * args.steps / float(te.item())
+    nk = int(h_cnt.sum().item())
+    e2e = {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
+           "d2h_bytes_per_step": int(4 * B + nk * 48 + nk * nf * 4)}
+
+    # ---- single-frame latency through Surfor::detectAndCompute (BASELINE: p50 ms/frame)
+    lat = None
+    if rank == 0:
+        one = sb.Surfor()
+        one.init(NOCT, THRESH, False, 9, 2, True, False, 4, W, H, max_pts=MAX_PTS, batch=1, device=local_rank)
+        data = sb.initSurfData(MAX_PTS, True, True, device=local_rank)
+        dd = torch.zeros((MAX_PTS, nf), dtype=torch.float32, device=dev)
+        ts = []
+        for i in range(20 + 100):
+            torch.cuda.synchronize()
+            a = time.perf_counter()
+            one.detectAndCompute(d_imgs[0], data, (W, H, pitch), desc_out=dd)
+            b = time.perf_counter()
+            if i >= 20:
+                ts.append((b - a) * 1e3)
+        lat = {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)), "keypoints": data.num_pts}
+        one.close()
+
+    # ---- CPU baseline (oracle port) on rank 0 at N=1 only: checker code, timed beside, never shipped
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        cores = os.cpu_count() or 1
+        n_s = int(min(max(2 * cores, 8), 96))
+        orc = ol.Oracle(NOCT, THRESH, False, 9, 2, True, False, 4)
+        sample = np.ascontiguousarray(frames[np.arange(n_s) % B])
+        secs, tot = orc.time_frames(sample, MAX_PTS, cores)
+        cpu = {"value": n_s / secs, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"{n_s} of the same 1080p frames, one frame per OpenMP worker, {secs:.1f} s"}
+
+    if rank == 0:
+        kpf = det.info.kernels_per_frame
+        line = {"metric": "frames/s SURF detect+describe @1080p", "value": value, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: synth_v1 1920x1080, 5 octaves x 5 layers, thresh 4, upright 64-d; "
+                                       f"batch of {B} distinct frames per GPU per step (configs[3] sharding)",
+                           "frames_per_step_per_gpu": B, "keypoints_per_frame": kp_mean,
+                           "l2_policy": f"inputs+intermediates per step {B * (W * H + 23.6e6) / 1e6:.0f} MB > 126 MB L2",
+                           "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+                "e2e": e2e, "gpu_launches": kpf * args.steps, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "latency": lat, "impl": "ours"}
+        print(json.dumps(line))
+    det.close()
+
+
+def run_reference(args, rank, world):
+    """The reference's own implementation on the same workload, rank 0 only."""
+    if rank != 0:
+        return
+    import cuda_surf_b200 as sb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    B = args.batch
+    frames = make_frames(min(B, POOL), sb)
+    cfg = {"workload": "BASELINE configs[1]: synth_v1 1920x1080, 5 octaves x 5 layers, thresh 4, upright 64-d",
+           "frames_per_step": len(frames)}
+    import ref_lib
+    have_gpu = False
+    if ref_lib.available():
+        try:
+            have_gpu = ref_lib.lib().ref_device_count() > 0
+        except OSError:
+            have_gpu = False
+    if have_gpu:
+        ref = ref_lib.Reference(W, H, NOCT, THRESH, False, 9, 2, True, False, 4)
+        per = []   # ms per frame, device-resident (as main.cpp:239-245)
+        per_e = []  # with H2D of the frame and D2H of points + descriptors
+        for step in range(args.warmup + args.steps):
+            ms_d = sum(float(ref.time_detect(f, MAX_PTS, 0, 1)[0][0]) for f in frames)
+            ms_e = sum(float(ref.time_detect_e2e(f, MAX_PTS, 0, 1)[0][0]) for f in frames)
+            if step >= args.warmup:
+                per.append(ms_d); per_e.append(ms_e)
+        ref.close()
+        ms_step = float(np.mean(per))
+        value = len(frames) / (ms_step / 1e3)
+        e2e_v = len(frames) / (float(np.mean(per_e)) / 1e3)
+        line = {"metric": "frames/s SURF detect+describe @1080p", "value": value, "unit": "frames/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic", "config": cfg,
+                "impl": "reference",
+                "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                 "sample": f"{len(frames)} frames per step through Surfor::detectAndCompute of the unmodified "
+                                           "reference built for sm_100a (oracle/_ref); it is a CUDA program, so it runs on "
+                                           "GPU 0 driven by one host thread"},
+                "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(len(frames) * W * H),
+                        "d2h_bytes_per_step": None}}
+        print(json.dumps(line))
+        return
+    # no reference library / no GPU: the CPU port of oracle/ on all host cores
+    import oracle_lib as ol
+    cores = os.cpu_count() or 1
+    orc = ol.Oracle(NOCT, THRESH, False, 9, 2, True, False, 4)
+    n_s = int(min(max(cores, 4), 64))
+    sample = np.ascontiguousarray(frames[np.arange(n_s) % len(frames)])
+    secs = []
+    for step in range(min(args.warmup, 1) + args.steps):
+        s, _ = orc.time_frames(sample, MAX_PTS, cores)
+        if step >= min(args.warmup, 1):
+            secs.append(s)
+    v = n_s / float(np.mean(secs))
+    line = {"metric": "frames/s SURF detect+describe @1080p", "value": v, "unit": "frames/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+            "config": cfg, "impl": "reference",
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_s} frames per step, one per OpenMP worker"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    try:
+        run_ours(args, rank, world, local_rank, dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,89 @@
+// common.cuh -- parameter blocks and device helpers shared by the sm_100a SURF kernels.
+//
+// Every kernel gets the whole per-context parameter block by value as a __grid_constant__
+// argument (constant bank, dynamically indexable), so there is no module-level device state:
+// contexts are independent (the reference keeps this in __constant__ symbols re-uploaded with
+// ~22 cudaMemcpyToSymbol per frame, surfd.cu:13-24, 2868-2871, 3072-3073).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "surfb200.h"
+
+namespace sb {
+
+constexpr int kMaxScale = 8;   // surfd.h:9
+constexpr int kMaxOctave = 8;  // surfd.h:10
+constexpr int kNBin = 72;      // surfd.h:11
+constexpr int kHwn = 6;        // surfd.h:14
+
+// One octave of the scale space (surf.cpp:240-294, surfd.cu:2844-2865, 3062-3073).
+struct OctaveP {
+    int sw, sh, sp;          // response dims and row pitch (floats)
+    int osz;                 // sh * sp : floats per layer
+    int s0, nl;              // first computed layer, number of computed layers
+    int octave;              // 1, 2, 4, ...
+    int delta;               // sampling * octave
+    long long resp_off;      // float offset of layer 0 inside one frame's response buffer
+    int l[kMaxScale];        // lobe per computed layer i (layer index s0+i)
+    int b1[kMaxScale];       // border actually computed per computed layer
+    float norm[kMaxScale];   // (9/l^2)^2
+    int borders[kMaxScale];  // lagged borders per layer index (d_borders of the reference)
+    int mb[4];               // NMS border per cell layer z (maximum_borders)
+    int nmb;
+    int hess_tile0, hess_tx, hess_ty;  // first linear tile id / tile grid of this octave (Hessian)
+    int nms_tile0, nms_tx, nms_ty;     // same for the NMS cell grid (per z)
+};
+
+struct PipeP {
+    // frame and buffers
+    int w, h;                 // image size
+    int iw, ih, ip;           // integral dims, pitch in ints
+    long long istride;        // ints per frame slot of the integral buffer (incl. 2 guard rows)
+    long long rstride;        // floats per frame slot of the response buffer
+    int nbands, nchunks;      // integral tiling: bands of kBandRows rows, chunks of 256 output columns
+    int band_rows;
+    // SurfParam (surf_structures.h:44-72)
+    float thresh, divisor;
+    int init_lobe, max_scale, noctaves, sampling;
+    int upright, extend, desc_wsz, mag_factor, orient_size, nfeatures;
+    int max_pts;
+    int hess_tiles, nms_tiles;  // total linear tiles per frame
+    OctaveP oct[kMaxOctave];
+    // exp tables of Surfor::initLut (surf.cpp:358-371) and the angle bins of surf.cpp:83-90
+    float lut1[83];
+    float lut2[40];
+    float bins[kNBin];
+};
+static_assert(sizeof(PipeP) <= 4000, "PipeP must fit the 4 KB kernel parameter space");
+
+// Inclusive pixel-box sum x in [xlo,xhi], y in [ylo,yhi] from the padded integral image
+// (I[y+1][x+1] = sum over pixels <= (x,y)); same four corners as getSum, surfd.cu:334-343.
+__device__ __forceinline__ int box_sum(const int* __restrict__ I, int ip, int xlo, int xhi, int ylo, int yhi) {
+    const int r1 = (yhi + 1) * ip, r0 = ylo * ip;
+    return __ldg(I + r1 + xhi + 1) + __ldg(I + r0 + xlo) - __ldg(I + r0 + xhi + 1) - __ldg(I + r1 + xlo);
+}
+
+// Haar wavelets of surfd.cu:1171-1182: upper-minus-lower and right-minus-left halves of the
+// (2s+1)^2 window centred at (x,y).
+__device__ __forceinline__ int haar_y(const int* __restrict__ I, int ip, int x, int y, int s) {
+    return box_sum(I, ip, x - s, x + s, y - s, y) - box_sum(I, ip, x - s, x + s, y, y + s);
+}
+__device__ __forceinline__ int haar_x(const int* __restrict__ I, int ip, int x, int y, int s) {
+    return box_sum(I, ip, x, x + s, y - s, y + s) - box_sum(I, ip, x - s, x, y - s, y + s);
+}
+
+// launchers (one translation unit per stage)
+cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
+                            int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);
+cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, float* d_resp, cudaStream_t st);
+cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
+                       int* d_counts, cudaStream_t st);
+cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
+                            const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
+                            cudaStream_t st);
+cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, cudaStream_t st);
+cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
+                         int nfeatures, cudaStream_t st);
+
+}  // namespace sb

@@ -1,0 +1,429 @@
+// ctx.cpp -- host side of libsurfb200.so: parameter derivation, buffer geometry, launch sequencing
+// and the extern "C" boundary declared in include/surfb200.h.
+//
+// Host logic replaced (reference file:line): Surfor::init (surf.cpp:60-91), initLut (:358-371),
+// allocMemory (:374-415), the octave loop of detectAndCompute (:240-294) with the per-layer
+// parameter derivation of cuCalcHessianMulti (surfd.cu:2844-2865) and cuFindMaximumWithInterp
+// (surfd.cu:3062-3073), the result copies (surf.cpp:302-303, 335-342, 421-427).
+// The reference re-derives and re-uploads all of this per octave per frame; here it is derived
+// once in sb_create into a PipeP block that every kernel receives by value, scratch is allocated
+// and zeroed once (valid regions are fully rewritten each frame, so the per-frame 23 MB memsets of
+// surf.cpp:345-349 are gone), and a frame is 5 kernel launches with no host round trip.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "surfb200.h"
+
+using namespace sb;
+
+struct sb_ctx {
+    sb_params prm{};
+    PipeP P{};
+    int device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    // scratch, `batch` frame slots each
+    int* d_integral = nullptr;
+    float* d_resp = nullptr;
+    int *d_colsum = nullptr, *d_rowsum = nullptr, *d_tilesum = nullptr;
+    int* d_counts = nullptr;
+    // staging for the synchronous / host-buffer entry points
+    uint8_t* d_stage_img = nullptr;
+    sb_point* d_stage_pts = nullptr;
+    float* d_stage_desc = nullptr;
+    int* h_counts = nullptr;          // pinned
+    sb_point* h_pts = nullptr;        // pinned, max_pts
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(sb_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_err = msg;
+    return code;
+}
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(ctx, SB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+static int align_up(int a, int b) { return (a % b) ? a - a % b + b : a; }
+
+// Derive the whole pipeline description. Returns SB_OK or an error code.
+static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
+    if (p.width < 32 || p.height < 32) { why = "frame smaller than 32x32"; return SB_ERR_INVALID; }
+    if (p.noctaves < 1 || p.noctaves > kMaxOctave) { why = "noctaves must be 1..8"; return SB_ERR_INVALID; }
+    if (p.doubled) { why = "doubled=true (2x up-sampled integral, surfd.cu:168-318) is not built yet"; return SB_ERR_UNSUPPORTED; }
+    if (p.sampling_step < 1 || p.desc_wsz < 1 || p.desc_wsz > 4 || 12 % p.desc_wsz) { why = "sampling_step>=1, desc_wsz in {1,2,3,4}"; return SB_ERR_INVALID; }
+    if (p.max_pts < 1 || p.batch < 1) { why = "max_pts and batch must be >= 1"; return SB_ERR_INVALID; }
+    if ((long long)p.width * p.height * 255 > 2147483647LL) { why = "frame too large for an int32 integral image"; return SB_ERR_INVALID; }
+    std::memset(&P, 0, sizeof(P));
+    // SurfParam, surf.cpp:66-79
+    P.divisor = 1.f;
+    P.init_lobe = p.init_mask_size / 3;
+    P.max_scale = P.init_lobe + 2;
+    P.noctaves = p.noctaves;
+    P.sampling = p.sampling_step;
+    P.thresh = p.thresh;
+    P.upright = p.upright ? 1 : 0;
+    P.extend = p.extend ? 1 : 0;
+    P.desc_wsz = p.desc_wsz;
+    P.mag_factor = 12 / p.desc_wsz;
+    P.orient_size = 4 + (p.extend ? 4 : 0);
+    P.nfeatures = p.desc_wsz * p.desc_wsz * P.orient_size;
+    P.max_pts = p.max_pts;
+    if (P.init_lobe < 1 || P.max_scale < 3 || P.max_scale > kMaxScale) { why = "init_mask_size must give 3..8 layers per octave"; return SB_ERR_INVALID; }
+    // geometry, surf.cpp:377-390
+    P.w = p.width; P.h = p.height;
+    P.iw = p.width + 1; P.ih = p.height + 1; P.ip = align_up(P.iw, 128);
+    P.istride = (long long)P.ip * (P.ih + 2);  // one zero guard row above and below
+    P.band_rows = 32;
+    P.nbands = (P.h + 31) / 32;
+    P.nchunks = (P.iw + 255) / 256;
+    int sw = (P.iw - 1) / P.sampling, sh = (P.ih - 1) / P.sampling;
+    long long roff = 0;
+    int hess_tiles = 0, nms_tiles = 0;
+    // octave schedule, surf.cpp:240-294 + surfd.cu:2844-2865
+    int mask = P.init_lobe - 2, octave = 1, s = 0, border1 = 0;
+    int borders[kMaxScale] = {0};
+    for (int o = 0; o < P.noctaves; o++) {
+        OctaveP& q = P.oct[o];
+        if (sw < 1 || sh < 1) { why = "too many octaves for this frame size"; return SB_ERR_INVALID; }
+        q.sw = sw; q.sh = sh; q.sp = align_up(sw, 128); q.osz = q.sh * q.sp;
+        q.octave = octave; q.delta = P.sampling * octave; q.resp_off = roff;
+        if (o > 0) {
+            border1 = ((3 * (mask + 4 * octave)) / 2) / (P.sampling * octave) + 1;
+            borders[0] = borders[1] = border1;
+            s = 2;
+        } else {
+            border1 = ((3 * (mask + 6 * octave)) / 2) / (P.sampling * octave) + 1;
+        }
+        q.s0 = s; q.nl = P.max_scale - s;
+        const int mask0 = mask;
+        for (int i = 0, ss = s; ss < P.max_scale; i++, ss++) {
+            borders[ss] = border1;  // stored before the update below: the one-layer lag of SURVEY.md 2.4-3
+            q.l[i] = mask0 + 2 * octave * (i + 1);
+            if (ss > 2) border1 = 3 * q.l[i] / 2 / q.delta + 1;
+            q.b1[i] = border1;
+            float nrm = 9.f / (float)(q.l[i] * q.l[i]);
+            nrm *= nrm;
+            q.norm[i] = nrm;
+            mask = q.l[i];
+        }
+        for (int k = 0; k < P.max_scale; k++) q.borders[k] = borders[k];
+        q.nmb = 0;
+        int mbmin = 1 << 30;
+        for (int k = 1; k < P.max_scale - 1; k += 2) {
+            q.mb[q.nmb] = borders[k + 1] + 1;
+            if (q.mb[q.nmb] < mbmin) mbmin = q.mb[q.nmb];
+            q.nmb++;
+        }
+        q.hess_tile0 = hess_tiles; q.hess_tx = (sw + 31) / 32; q.hess_ty = (sh + 7) / 8;
+        hess_tiles += q.hess_tx * q.hess_ty;
+        const int cw = (sw - 2 * mbmin + 1) / 2, ch = (sh - 2 * mbmin + 1) / 2;  // 2x2 cells per row / column
+        q.nms_tile0 = nms_tiles;
+        q.nms_tx = cw > 0 ? (cw + 31) / 32 : 0;
+        q.nms_ty = ch > 0 ? (ch + 7) / 8 : 0;
+        if (q.nms_tx == 0 || q.nms_ty == 0) { q.nms_tx = 1; q.nms_ty = 1; }  // keep the tile table monotone
+        nms_tiles += q.nmb * q.nms_tx * q.nms_ty;
+        roff += (long long)P.max_scale * q.osz;
+        octave += octave;
+        sw >>= 1; sh >>= 1;
+    }
+    P.rstride = roff;
+    P.hess_tiles = hess_tiles;
+    P.nms_tiles = nms_tiles;
+    // tables: surf.cpp:358-371 (expf on the host, as the reference) and surf.cpp:83-90
+    for (int n = 0; n < 83; n++) P.lut1[n] = expf(-(n + 0.5f) / 12.5f);
+    for (int n = 0; n < 40; n++) P.lut2[n] = expf(-(n + 0.5f) / 8.f);
+    P.bins[0] = (float)(-3.1415926535897932384626433832795);
+    for (int i = 1; i < kNBin; i++) P.bins[i] = P.bins[i - 1] + 0.08726646259971647f;
+    return SB_OK;
+}
+
+extern "C" const char* sb_last_error(const sb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" void sb_destroy(sb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_integral); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
+    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_stage_img); cudaFree(ctx->d_stage_pts);
+    cudaFree(ctx->d_stage_desc);
+    if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+    if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
+    sb_ctx* ctx = nullptr;  // errors before allocation go to the thread-local slot
+    if (!out || !params) return fail(nullptr, SB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    PipeP P;
+    std::string why;
+    const int rc = build_pipe(*params, P, why);
+    if (rc != SB_OK) return fail(nullptr, rc, why);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, SB_ERR_CUDA, "no CUDA device: libsurfb200 has no CPU fallback");
+    if (params->device < 0 || params->device >= ndev) return fail(nullptr, SB_ERR_INVALID, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, params->device) != cudaSuccess) return fail(nullptr, SB_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, SB_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; kernels are built for sm_100a only");
+    if (cudaSetDevice(params->device) != cudaSuccess) return fail(nullptr, SB_ERR_CUDA, "cudaSetDevice failed");
+
+    sb_ctx* c = new sb_ctx;
+    c->prm = *params; c->P = P; c->device = params->device; c->sm_count = prop.multiProcessorCount;
+    const int B = params->batch;
+    const size_t isz = sizeof(int) * (size_t)P.istride * B;
+    const size_t rsz = sizeof(float) * (size_t)P.rstride * B;
+    const size_t tsz = sizeof(int) * (size_t)P.nbands * P.nchunks * 256 * B;
+    const size_t rowsz = sizeof(int) * (size_t)P.nbands * 32 * P.nchunks * B;
+    const size_t ttsz = sizeof(int) * (size_t)P.nbands * P.nchunks * B;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    ok(cudaMalloc((void**)&c->d_integral, isz));
+    ok(cudaMalloc((void**)&c->d_resp, rsz));
+    ok(cudaMalloc((void**)&c->d_colsum, tsz));
+    ok(cudaMalloc((void**)&c->d_rowsum, rowsz));
+    ok(cudaMalloc((void**)&c->d_tilesum, ttsz));
+    ok(cudaMalloc((void**)&c->d_counts, sizeof(int) * B));
+    ok(cudaMallocHost((void**)&c->h_counts, sizeof(int) * B));
+    ok(cudaMallocHost((void**)&c->h_pts, sizeof(sb_point) * (size_t)P.max_pts));
+    if (e == cudaSuccess) {
+        // zeroed once: borders of every response layer, row/column 0, padding and guard rows of
+        // the integral are never written afterwards
+        ok(cudaMemsetAsync(c->d_integral, 0, isz, c->stream));
+        ok(cudaMemsetAsync(c->d_resp, 0, rsz, c->stream));
+        ok(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * B, c->stream));
+        ok(cudaStreamSynchronize(c->stream));
+    }
+    if (e != cudaSuccess) {
+        g_create_err = std::string("allocation failed: ") + cudaGetErrorString(e);
+        sb_destroy(c);
+        return e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA;
+    }
+    (void)ctx;
+    *out = c;
+    return SB_OK;
+}
+
+extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
+    if (!ctx || !info) return SB_ERR_INVALID;
+    const PipeP& P = ctx->P;
+    std::memset(info, 0, sizeof(*info));
+    info->max_scale = P.max_scale; info->nfeatures = P.nfeatures;
+    info->iw = P.iw; info->ih = P.ih; info->ipitch = P.ip;
+    long long t = 0;
+    for (int o = 0; o < P.noctaves; o++) {
+        info->sw[o] = P.oct[o].sw; info->sh[o] = P.oct[o].sh; info->sp[o] = P.oct[o].sp;
+        t += (long long)P.max_scale * P.oct[o].sw * P.oct[o].sh;
+    }
+    info->resp_floats = t;
+    info->kernels_per_frame = 2 /*integral*/ + 1 /*hessian*/ + 1 /*nms*/ + 1 /*clamp*/ + (P.upright ? 1 : 2);
+    return SB_OK;
+}
+
+// Enqueue integral -> Hessian -> NMS(+refine, append) -> clamp [-> orientation] -> descriptors.
+// ev: optional 5 events recorded at the stage boundaries (profiling entry point only).
+static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
+                          sb_point* d_points, int* d_counts, float* d_desc, cudaStream_t st, cudaEvent_t* ev = nullptr) {
+    const PipeP& P = ctx->P;
+    CU(cudaMemsetAsync(d_counts, 0, sizeof(int) * nframes, st));
+    if (ev) CU(cudaEventRecord(ev[0], st));
+    CU(launch_integral(P, d_images, image_stride, pitch, nframes, ctx->d_integral, ctx->d_colsum, ctx->d_rowsum, ctx->d_tilesum, st));
+    if (ev) CU(cudaEventRecord(ev[1], st));
+    CU(launch_hessian(P, nframes, ctx->d_integral, ctx->d_resp, st));
+    if (ev) CU(cudaEventRecord(ev[2], st));
+    CU(launch_nms(P, nframes, ctx->d_integral, ctx->d_resp, d_points, d_counts, st));
+    CU(launch_clamp_counts(d_counts, nframes, P.max_pts, st));
+    if (ev) CU(cudaEventRecord(ev[3], st));
+    if (d_desc)
+        CU(launch_describe(P, nframes, ctx->d_integral, d_points, P.max_pts, d_counts, -1, d_desc,
+                           (long long)P.max_pts * P.nfeatures, ctx->sm_count, st));
+    if (ev) CU(cudaEventRecord(ev[4], st));
+    return SB_OK;
+}
+
+extern "C" int sb_detect_batch_profile(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
+                                       sb_point* d_points, int* d_counts, float* d_desc, void* stream, float* stage_ms) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (!d_images || !d_points || !d_counts || !stage_ms || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->P.w)
+        return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_profile: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&ev[i]));
+    int rc = enqueue_frames(ctx, d_images, image_stride, pitch, nframes, d_points, d_counts, d_desc, st, ev);
+    if (rc == SB_OK) {
+        cudaError_t e = cudaEventSynchronize(ev[4]);
+        for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+        if (e != cudaSuccess) rc = fail(ctx, SB_ERR_CUDA, cudaGetErrorString(e));
+    }
+    for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+extern "C" int sb_detect_batch_async(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
+                                     sb_point* d_points, int* d_counts, float* d_desc, void* stream) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (!d_images || !d_points || !d_counts || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->P.w)
+        return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_async: bad argument (nframes must be 1..batch, pitch >= width)");
+    CU(cudaSetDevice(ctx->device));
+    return enqueue_frames(ctx, d_images, image_stride, pitch, nframes, d_points, d_counts, d_desc,
+                          stream ? (cudaStream_t)stream : ctx->stream);
+}
+
+extern "C" int sb_sync(sb_ctx* ctx) {
+    if (!ctx) return SB_ERR_INVALID;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}
+
+extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w, int h, int pitch, sb_point* d_points,
+                                     sb_point* h_points, int max_pts, int* num_pts, float** d_desc_addr, int want_desc) {
+    if (!ctx) return SB_ERR_INVALID;
+    const PipeP& P = ctx->P;
+    if (!d_image || !d_points || !num_pts) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: null argument");
+    if (w != P.w || h != P.h) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: frame size differs from the context's (create one context per size)");
+    if (max_pts != P.max_pts) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: max_pts differs from the context's");
+    if (pitch < w) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: pitch < width");
+    CU(cudaSetDevice(ctx->device));
+    float* d_desc = nullptr;
+    if (want_desc && d_desc_addr) {
+        if (!*d_desc_addr) {
+            // like the reference (surfd.cu:3264) the callee allocates and the caller cudaFree's; unlike
+            // it, a non-NULL *d_desc_addr (the buffer of the previous call, main.cpp:241-245) is reused
+            float* buf = nullptr;
+            CU(cudaMalloc((void**)&buf, sizeof(float) * (size_t)P.max_pts * P.nfeatures));
+            *d_desc_addr = buf;
+        }
+        d_desc = *d_desc_addr;
+    }
+    cudaStream_t st = ctx->stream;
+    const int rc = enqueue_frames(ctx, d_image, 0, pitch, 1, d_points, ctx->d_counts, d_desc, st);
+    if (rc != SB_OK) return rc;
+    CU(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int n = ctx->h_counts[0];
+    *num_pts = n;
+    if (h_points && n > 0) {
+        CU(cudaMemcpyAsync(ctx->h_pts, d_points, sizeof(sb_point) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        // the reference copies the first 6 (7 with orientation) 4-byte fields of each point, surf.cpp:339
+        const size_t nb = sizeof(float) * ((want_desc && !P.upright) ? 7 : 6);
+        for (int i = 0; i < n; i++) std::memcpy(&h_points[i], &ctx->h_pts[i], nb);
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, sb_point* h_points, int* h_counts,
+                                    float* h_desc) {
+    if (!ctx) return SB_ERR_INVALID;
+    const PipeP& P = ctx->P;
+    if (!h_images || !h_points || !h_counts || nframes < 1 || nframes > ctx->prm.batch)
+        return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_host: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const int B = ctx->prm.batch;
+    const size_t fbytes = (size_t)P.w * P.h;
+    const int dpitch = align_up(P.w, 128);
+    const size_t dstride = (size_t)dpitch * P.h;
+    if (!ctx->d_stage_img) {
+        CU(cudaMalloc((void**)&ctx->d_stage_img, dstride * B));
+        CU(cudaMemset(ctx->d_stage_img, 0, dstride * B));
+        CU(cudaMalloc((void**)&ctx->d_stage_pts, sizeof(sb_point) * (size_t)P.max_pts * B));
+        CU(cudaMalloc((void**)&ctx->d_stage_desc, sizeof(float) * (size_t)P.max_pts * P.nfeatures * B));
+    }
+    cudaStream_t st = ctx->stream;
+    if (dpitch == P.w) {
+        CU(cudaMemcpyAsync(ctx->d_stage_img, h_images, fbytes * nframes, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < nframes; f++)
+            CU(cudaMemcpy2DAsync(ctx->d_stage_img + f * dstride, dpitch, h_images + f * fbytes, P.w, P.w, P.h,
+                                 cudaMemcpyHostToDevice, st));
+    }
+    const int rc = enqueue_frames(ctx, ctx->d_stage_img, dstride, dpitch, nframes, ctx->d_stage_pts, ctx->d_counts,
+                                  h_desc ? ctx->d_stage_desc : nullptr, st);
+    if (rc != SB_OK) return rc;
+    CU(cudaMemcpyAsync(h_counts, ctx->d_counts, sizeof(int) * nframes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // second leg: only the keypoints that exist
+    for (int f = 0; f < nframes; f++) {
+        const int n = h_counts[f];
+        if (n <= 0) continue;
+        CU(cudaMemcpyAsync(h_points + (size_t)f * P.max_pts, ctx->d_stage_pts + (size_t)f * P.max_pts, sizeof(sb_point) * n,
+                           cudaMemcpyDeviceToHost, st));
+        if (h_desc)
+            CU(cudaMemcpyAsync(h_desc + (size_t)f * P.max_pts * P.nfeatures, ctx->d_stage_desc + (size_t)f * P.max_pts * P.nfeatures,
+                               sizeof(float) * (size_t)n * P.nfeatures, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+extern "C" int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const float* d_feat1,
+                        const sb_point* d_pts2, int n2, const float* d_feat2) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (n1 < 0 || n2 < 0 || (n1 > 0 && (!d_pts1 || !d_feat1)) || (n2 > 0 && (!d_pts2 || !d_feat2)))
+        return fail(ctx, SB_ERR_INVALID, "sb_match: bad argument");
+    if (n1 == 0) return SB_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(launch_match(d_pts1, n1, d_feat1, d_pts2, n2, d_feat2, ctx->P.nfeatures, st));
+    if (h_pts1) {
+        // the five match fields start at SurfPoint::score (surf.cpp:421-425)
+        const size_t off = offsetof(sb_point, score);
+        CU(cudaMemcpy2DAsync((char*)h_pts1 + off, sizeof(sb_point), (const char*)d_pts1 + off, sizeof(sb_point),
+                             5 * sizeof(float), n1, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return SB_OK;
+}
+
+extern "C" int sb_get_integral(sb_ctx* ctx, int slot, int32_t* h_out) {
+    if (!ctx || !h_out || slot < 0 || slot >= ctx->prm.batch) return SB_ERR_INVALID;
+    const PipeP& P = ctx->P;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy2D(h_out, sizeof(int) * P.iw, ctx->d_integral + (size_t)slot * P.istride + P.ip, sizeof(int) * P.ip,
+                    sizeof(int) * P.iw, P.ih, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+extern "C" int sb_get_response(sb_ctx* ctx, int slot, float* h_out) {
+    if (!ctx || !h_out || slot < 0 || slot >= ctx->prm.batch) return SB_ERR_INVALID;
+    const PipeP& P = ctx->P;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float* dst = h_out;
+    for (int o = 0; o < P.noctaves; o++) {
+        const OctaveP& q = P.oct[o];
+        for (int s = 0; s < P.max_scale; s++) {
+            CU(cudaMemcpy2D(dst, sizeof(float) * q.sw, ctx->d_resp + (size_t)slot * P.rstride + q.resp_off + (size_t)s * q.osz,
+                            sizeof(float) * q.sp, sizeof(float) * q.sw, q.sh, cudaMemcpyDeviceToHost));
+            dst += (size_t)q.sw * q.sh;
+        }
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_describe(sb_ctx* ctx, int slot, sb_point* d_points, int n, float* d_desc) {
+    if (!ctx || slot < 0 || slot >= ctx->prm.batch || n < 0 || (n > 0 && (!d_points || !d_desc))) return SB_ERR_INVALID;
+    if (n == 0) return SB_OK;
+    const PipeP& P = ctx->P;
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_describe(P, 1, ctx->d_integral + (size_t)slot * P.istride, d_points, 0, nullptr, n, d_desc, 0, ctx->sm_count, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SB_OK;
+}

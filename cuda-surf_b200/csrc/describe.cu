@@ -1,0 +1,346 @@
+// describe.cu -- Haar-wavelet orientation assignment and the 4x4x{4,8} SURF descriptor with fused
+// L2 normalisation, ONE WARP PER KEYPOINT.
+//
+// Replaces cuDescribe (surfd.cu:3251-3325) and its kernels:
+//   assignOrientationApprox (surfd.cu:1711-1960), describeURWithoutNormalization (:1566-1615),
+//   describeApproxWithoutNormalization (:2391-2444), normalize (:2447-2493).
+// The reference sizes a (32x32)-thread grid per keypoint from a global max radius read back to the
+// host, scatters every sample into the 64 output floats with float atomicAdd in GLOBAL memory
+// (placeInIndex, :1199-1271), then normalises in a third launch. Here:
+//   * the keypoint count is read on the device (no host round trip, no cudaMalloc per frame);
+//   * a warp walks its keypoint's own (2R+1)^2 sampling lattice, lanes along the lattice row so
+//     the integral-image gathers of neighbouring lanes share cache lines;
+//   * each lane accumulates into a private copy of the descriptor in shared memory laid out
+//     [element][lane] (bank == lane: conflict-free, no atomics, deterministic), reduced across
+//     lanes with a rotated read, squared-summed with shuffles and normalised in registers;
+//   * descriptors leave the SM once, as 128-byte coalesced stores.
+// Arithmetic (rounding modes, FMA placement, IEEE division, __sinf/__cosf) follows the reference
+// so that descriptors agree to float round-off.
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int kWarpsPerCta = 4;
+constexpr float kR255 = 0.003921568627f;
+constexpr float kWindow = 1.0471975511965976f;     // surfd.h:12
+constexpr float kSepAngle = 0.08726646259971647f;  // surfd.h:13
+constexpr float kHalfPi = 1.5707963267948966f;     // cuda_utils.h:8 (float)
+constexpr double kPi = 3.14159265358979323846;     // M_PI (double in the reference)
+constexpr int kORadius = 9;                        // surfd.h:15
+constexpr int kOSide = 2 * kORadius + 1;           // 19
+constexpr int kOSamples = kOSide * kOSide;         // 361
+constexpr int kPasz = kNBin + 2 * kHwn;            // 84
+
+// ---------------------------------------------------------------------------------- orientation
+
+// dFastAtan2, surfd.cu:114-126 (H_PI float, M_PI double).
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float a = __fdiv_rn(fminf(ax, ay), fmaxf(ax, ay));
+    const float s = __fmul_rn(a, a);
+    float r = __fmaf_rn(__fmaf_rn(__fmaf_rn(-0.0464964749f, s, 0.15931422f), s, -0.327622764f), __fmul_rn(s, a), a);
+    r = (ay > ax) ? __fsub_rn(kHalfPi, r) : r;
+    r = (x < 0.f) ? (float)(kPi - (double)r) : r;
+    r = (y < 0.f) ? -r : r;
+    return r;
+}
+
+struct OrientSmem {
+    float ang[kOSamples];
+    float ps[kOSamples];
+    short hid[kOSamples + 1];
+    int hist[kNBin];
+    float avg[kNBin];
+    float psum[kNBin];
+    float pas[kPasz];
+    float ws[kNBin];
+    float was[kNBin];
+};
+
+// grid (ctas, nframes), 4 warps per CTA, warp per keypoint. Deterministic: samples are binned
+// in lattice scan order (the reference's shared-memory atomics make its sums order-dependent).
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb_point* __restrict__ points,
+              long long pts_stride, const int* __restrict__ counts, int fixed_count) {
+    __shared__ OrientSmem sm[kWarpsPerCta];
+    __shared__ float s_lut1[83];
+    const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = threadIdx.x; t < 83; t += blockDim.x) s_lut1[t] = P.lut1[t];
+    __syncthreads();
+    const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
+    const int* I = Ibase + (size_t)f * P.istride + P.ip;
+    sb_point* pts = points + (size_t)f * pts_stride;
+    OrientSmem& S = sm[warp];
+
+    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
+        const float x = pts[pi].x, y = pts[pi].y, scale = pts[pi].scale;
+        const int hs = __float2int_rz(__fmaf_rn(2.f, scale, 1.6f));
+        const int st = __float2int_rz(__fadd_rn(scale, 0.8f));
+        const int ixc = __float2int_rn(x), iyc = __float2int_rn(y);
+        // phase A: Haar responses on the 19x19 lattice
+        for (int qi = lane; qi < kOSamples; qi += 32) {
+            const int y1 = qi / kOSide - kORadius, x1 = qi % kOSide - kORadius;
+            const int xx = ixc + x1 * st, yy = iyc + y1 * st;
+            short hid = -1;
+            float angle = 0.f, psum = 0.f;
+            const int distsq = y1 * y1 + x1 * x1;
+            if (yy + hs + 2 < P.ih && yy - hs > -1 && xx + hs + 2 < P.iw && xx - hs > -1 && distsq < 82) {
+                const float dx = __fmul_rn(__int2float_rn(haar_x(I, P.ip, xx, yy, hs)), kR255);
+                const float dy = __fmul_rn(__int2float_rn(haar_y(I, P.ip, xx, yy, hs)), kR255);
+                const float mag = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                if (mag > 0.f) {
+                    angle = fast_atan2(dy, dx);
+                    hid = (short)(__float2int_rz((float)(((double)angle + kPi) / (double)kSepAngle)) % kNBin);
+                    psum = __fmul_rn(s_lut1[distsq], mag);
+                }
+            }
+            S.hid[qi] = hid; S.ang[qi] = angle; S.ps[qi] = psum;
+        }
+        __syncwarp();
+        // phase B: per-bin sums in scan order; lane owns bins lane, lane+32, lane+64
+        for (int b = lane; b < kNBin; b += 32) {
+            int cnt = 0;
+            float A = 0.f, Psum = 0.f, Q = 0.f, Qw = 0.f;
+            for (int qi = 0; qi < kOSamples; qi++) {
+                if (S.hid[qi] == b) {
+                    const float angle = S.ang[qi], ps = S.ps[qi];
+                    cnt++;
+                    A = __fadd_rn(A, angle);
+                    Psum = __fadd_rn(Psum, ps);
+                    Q = __fadd_rn(Q, __fmul_rn(angle, ps));
+                    if (b < kHwn) Qw = __fadd_rn(Qw, (float)(((double)angle + 2 * kPi) * (double)ps));
+                    else if (b + kHwn >= kNBin) Qw = __fadd_rn(Qw, (float)(((double)angle - 2 * kPi) * (double)ps));
+                }
+            }
+            S.hist[b] = cnt;
+            S.avg[b] = cnt > 0 ? __fdiv_rn(A, __int2float_rn(cnt)) : P.bins[b];
+            S.psum[b] = Psum;
+            S.pas[b + kHwn] = Q;
+            if (b < kHwn) S.pas[b + kHwn + kNBin] = Qw;
+            else if (b + kHwn >= kNBin) S.pas[b + kHwn - kNBin] = Qw;
+        }
+        __syncwarp();
+        // phase C: 60-degree sliding window (+-5 full bins, fractional edge bins), surfd.cu:1848-1908
+        for (int i = lane; i < kNBin; i += 32) {
+            float ws = 0.f, was = 0.f;
+            const float avg_i = S.avg[i];
+            for (int j = -kHwn; j <= kHwn; j++) {
+                int k = i + j;
+                if (j == -kHwn) {
+                    float res;
+                    if (k < 0) {
+                        k += kNBin;
+                        const int k1 = (k + 1) % kNBin;
+                        const float b1 = P.bins[k1];
+                        res = (float)((double)__fsub_rn(__fadd_rn(b1, kWindow / 2), avg_i) - (b1 < 0.f ? 0.0 : 2 * kPi));
+                    } else {
+                        res = __fsub_rn(__fadd_rn(P.bins[k + 1], kWindow / 2), avg_i);
+                    }
+                    const float er = __fdiv_rn(res, kSepAngle);
+                    ws = __fadd_rn(ws, __fmul_rn(er, S.psum[k]));
+                    was = __fadd_rn(was, __fmul_rn(er, S.pas[i]));
+                } else if (j == kHwn) {
+                    float res;
+                    if (k >= kNBin) {
+                        k -= kNBin;
+                        res = (float)((double)__fadd_rn(avg_i, kWindow / 2) - 2 * kPi - (double)P.bins[k]);
+                    } else {
+                        res = __fsub_rn(__fadd_rn(avg_i, kWindow / 2), P.bins[k]);
+                    }
+                    const float er = __fdiv_rn(res, kSepAngle);
+                    ws = __fadd_rn(ws, __fmul_rn(er, S.psum[k]));
+                    was = __fadd_rn(was, __fmul_rn(er, S.pas[i + 2 * kHwn]));
+                } else {
+                    was = __fadd_rn(was, S.pas[k + kHwn]);
+                    if (k < 0) k += kNBin; else if (k >= kNBin) k -= kNBin;
+                    ws = __fadd_rn(ws, S.psum[k]);
+                }
+            }
+            S.ws[i] = ws; S.was[i] = was;
+        }
+        __syncwarp();
+        // phase D: the reference's tournament arg-max (64-wide tree, 8-wide tree at 64, strict <)
+        if (lane == 0) {
+            int residual = kNBin, offset = 0;
+            while (residual > 0) {
+                int zn = 1;
+                while (zn * 2 <= residual) zn *= 2;
+                for (int stride = zn / 2; stride > 0; stride >>= 1)
+                    for (int t = 0; t < stride; t++) {
+                        const int id1 = t + offset, id2 = id1 + stride;
+                        if (S.ws[id1] < S.ws[id2]) { S.ws[id1] = S.ws[id2]; S.was[id1] = S.was[id2]; }
+                    }
+                if (S.ws[0] < S.ws[offset]) { S.ws[0] = S.ws[offset]; S.was[0] = S.was[offset]; }
+                residual -= zn;
+                offset += zn;
+            }
+            pts[pi].ori = __fdiv_rn(S.was[0], S.ws[0]);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------- descriptor
+
+// One sample's bilinear spread into the 2x2 nearest cells (placeInIndex, surfd.cu:1199-1271),
+// into this lane's private descriptor copy h[element*32 + lane].
+__device__ __forceinline__ void place(float* __restrict__ h, int lane, int W, int O, float mag1, int ori1, float mag2,
+                                      int ori2, float rx, float cx) {
+    const int ri = __float2int_rz(rx >= 0.f ? rx : __fsub_rn(rx, 1.f));
+    const int ci = __float2int_rz(cx >= 0.f ? cx : __fsub_rn(cx, 1.f));
+    const float rfrac = __fsub_rn(rx, __int2float_rn(ri));
+    const float cfrac = __fsub_rn(cx, __int2float_rn(ci));
+    const float cfrac1 = __fsub_rn(1.f, cfrac);
+    if (ri >= 0) {
+        const float rw1 = __fmul_rn(mag1, __fsub_rn(1.f, rfrac)), rw2 = __fmul_rn(mag2, __fsub_rn(1.f, rfrac));
+        if (ci >= 0) {
+            float* e = h + ((ri * W + ci) * O) * 32 + lane;
+            e[ori1 * 32] += __fmul_rn(rw1, cfrac1);
+            e[ori2 * 32] += __fmul_rn(rw2, cfrac1);
+        }
+        if (ci + 1 < W) {
+            float* e = h + ((ri * W + ci + 1) * O) * 32 + lane;
+            e[ori1 * 32] += __fmul_rn(rw1, cfrac);
+            e[ori2 * 32] += __fmul_rn(rw2, cfrac);
+        }
+    }
+    if (ri + 1 < W) {
+        const float rw1 = __fmul_rn(mag1, rfrac), rw2 = __fmul_rn(mag2, rfrac);
+        if (ci >= 0) {
+            float* e = h + (((ri + 1) * W + ci) * O) * 32 + lane;
+            e[ori1 * 32] += __fmul_rn(rw1, cfrac1);
+            e[ori2 * 32] += __fmul_rn(rw2, cfrac1);
+        }
+        if (ci + 1 < W) {
+            float* e = h + (((ri + 1) * W + ci + 1) * O) * 32 + lane;
+            e[ori1 * 32] += __fmul_rn(rw1, cfrac);
+            e[ori2 * 32] += __fmul_rn(rw2, cfrac);
+        }
+    }
+}
+
+// grid (ctas, nframes), 4 warps per CTA, dynamic smem = 4 * NF*32 floats + 40 floats.
+template <bool UPRIGHT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+describe_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
+                long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
+                long long desc_stride) {
+    extern __shared__ float smem[];
+    const int NF = P.nfeatures, W = P.desc_wsz, O = P.orient_size;
+    const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_lut2 = smem + kWarpsPerCta * NF * 32;
+    for (int t = threadIdx.x; t < 40; t += blockDim.x) s_lut2[t] = P.lut2[t];
+    __syncthreads();
+    float* h = smem + warp * NF * 32;
+    const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
+    const int* I = Ibase + (size_t)f * P.istride + P.ip;
+    const sb_point* pts = points + (size_t)f * pts_stride;
+    float* dout = desc + (size_t)f * desc_stride;
+    const float fW = __int2float_rn(W);
+
+    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
+        for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
+        const float x = pts[pi].x, y = pts[pi].y;
+        const float sc = __fmul_rn(1.65f, pts[pi].scale);
+        const int step = max(__float2int_rn(__fmul_rn(sc, 0.5f)), 1);
+        const int ixc = __float2int_rn(x), iyc = __float2int_rn(y);
+        const float fx = __fsub_rn(x, __int2float_rn(ixc)), fy = __fsub_rn(y, __int2float_rn(iyc));
+        const float spacing = __fmul_rn(sc, __int2float_rn(P.mag_factor));
+        const int S = __float2int_rz(sc);
+        const float wofs = __fmaf_rn(fW, 0.5f, -0.5f);
+        const float fstep = __int2float_rn(step);
+        float sine = 0.f, cose = 1.f, fracr = fy, fracc = fx;
+        int R;
+        if (UPRIGHT) {
+            R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(spacing, __int2float_rn(W + 1)), 0.5f), fstep));
+        } else {
+            const float ori = pts[pi].ori;
+            sine = __sinf(ori);
+            cose = __cosf(ori);
+            fracc = __fmaf_rn(-sine, fy, __fmul_rn(cose, fx));
+            fracr = __fmaf_rn(cose, fy, __fmul_rn(sine, fx));
+            R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(1.4f, spacing), __int2float_rn(W + 1)), 0.5f), fstep));
+        }
+        const int side = 2 * R + 1, total = side * side;
+        const float inv_side = 1.f / (float)side;
+        for (int qi = lane; qi < total; qi += 32) {
+            const int ii = (int)(((float)qi + 0.5f) * inv_side);
+            const int i = ii - R, j = qi - ii * side - R;
+            float rpos, cpos;
+            if (UPRIGHT) {
+                rpos = __fdiv_rn(__fsub_rn(__int2float_rn(step * i), fy), spacing);
+                cpos = __fdiv_rn(__fsub_rn(__int2float_rn(step * j), fx), spacing);
+            } else {
+                const float fi = __int2float_rn(i), fj = __int2float_rn(j);
+                rpos = __fdiv_rn(__fmaf_rn(fstep, __fmaf_rn(cose, fi, __fmul_rn(sine, fj)), -fracr), spacing);
+                cpos = __fdiv_rn(__fmaf_rn(fstep, __fmaf_rn(-sine, fi, __fmul_rn(cose, fj)), -fracc), spacing);
+            }
+            const float rx = __fadd_rn(rpos, wofs), cx = __fadd_rn(cpos, wofs);
+            if (!(rx > -1.f && rx < fW && cx > -1.f && cx < fW)) continue;
+            const int r = iyc + i * step, c = ixc + j * step;
+            if (!(r >= 1 + S && r < P.ih - 1 - S && c >= 1 + S && c < P.iw - 1 - S)) continue;
+            const float weight = s_lut2[__float2int_rz(__fmaf_rn(rpos, rpos, __fmul_rn(cpos, cpos)))];
+            const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_x(I, P.ip, c, r, S))), kR255);
+            const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_y(I, P.ip, c, r, S))), kR255);
+            float dx = a, dy = b;
+            if (!UPRIGHT) {
+                dx = __fmaf_rn(cose, a, __fmul_rn(sine, b));
+                dy = __fmaf_rn(sine, a, -__fmul_rn(cose, b));
+            }
+            if (O == 4) {
+                place(h, lane, W, O, dx, (dx < 0.f ? 0 : 1), dy, (dy < 0.f ? 2 : 3), rx, cx);
+            } else {
+                place(h, lane, W, O, dx, (dy < 0.f ? 0 : 1), fabsf(dx), (dy < 0.f ? 2 : 3), rx, cx);
+                place(h, lane, W, O, dy, (dx < 0.f ? 4 : 5), fabsf(dy), (dx < 0.f ? 6 : 7), rx, cx);
+            }
+        }
+        __syncwarp();
+        // reduce the 32 private copies (rotated read: bank == (lane + k) % 32), normalise, store
+        float v[4];
+        float sq = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = lane + 32 * u;
+            float acc = 0.f;
+            if (e < NF) {
+                for (int k = 0; k < 32; k++) acc += h[e * 32 + ((lane + k) & 31)];
+            }
+            v[u] = acc;
+            sq = __fmaf_rn(acc, acc, sq);
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
+        const float inv = __fdiv_rn(1.f, __fsqrt_rn(sq));
+        float* d = dout + (size_t)pi * NF;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = lane + 32 * u;
+            if (e < NF) d[e] = __fmul_rn(v[u], inv);
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
+                            const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
+                            cudaStream_t st) {
+    const int maxn = fixed_count >= 0 ? fixed_count : P.max_pts;
+    if (maxn <= 0 || nframes <= 0) return cudaSuccess;
+    const int need = (maxn + kWarpsPerCta - 1) / kWarpsPerCta;
+    int ctas = (sm_count * 8 + nframes - 1) / nframes;
+    if (ctas < 32) ctas = 32;
+    if (ctas > need) ctas = need;
+    const dim3 grid(ctas, nframes), block(kWarpsPerCta * 32);
+    if (!P.upright) orient_kernel<<<grid, block, 0, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count);
+    const size_t smem = ((size_t)kWarpsPerCta * P.nfeatures * 32 + 40) * sizeof(float);
+    if (P.upright) {
+        cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        describe_kernel<true><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+    } else {
+        cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        describe_kernel<false><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sb

@@ -1,0 +1,202 @@
+// integral.cu -- padded integral image, u8 -> int32, I[y+1][x+1] = sum_{j<=y,i<=x} img[j][i].
+//
+// Replaces cuIntegral = integralRow + integralCol (surfd.cu:129-165, 2683-2704): the reference runs
+// one thread per image row, then one thread per column, each a serial loop over the other
+// dimension. Here the image is cut into tiles of kBand rows x 256 output columns and the 2-D
+// prefix is done reduce-then-scan:
+//   pass A (integral_reduce): per tile, column sums T[band][X], row sums R[y][chunk] and the tile
+//          total TT[band][chunk]                      -- reads the image once (HBM), writes ~4 %.
+//   pass B (integral_scan):   per tile, carry row = look-back over T/TT of the bands above,
+//          warp-shuffle row scans (8 px per lane from one 64-bit load), shared-memory column
+//          scan, coalesced 128-byte row stores      -- re-reads the image from L2, writes the
+//          integral exactly once.
+// Compulsory traffic is img + integral; the reference moves the integral three times.
+// Chunks are aligned in OUTPUT columns (X = x+1), so every integral row store is a full 128-byte
+// line; the one-byte shift lands on the (cheap) image loads instead.
+#include "common.cuh"
+
+namespace sb {
+
+constexpr int kBand = 32;     // rows per tile
+constexpr int kChunk = 256;   // output columns per tile
+constexpr int kThreads = 256;
+
+// 8 pixels for output columns X = 256c + 8*lane + k  (image column X-1), zero outside the image.
+template <bool ALIGNED>
+__device__ __forceinline__ void load_shifted(const uint8_t* __restrict__ row, int w, int c, int lane, int (&v)[8]) {
+    const int x0 = kChunk * c + 8 * lane;  // first image column of this lane's aligned 8-byte group
+    unsigned lo = 0, hi = 0;
+    if (ALIGNED && x0 + 7 < w) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(row + x0));
+        lo = a.x; hi = a.y;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (x0 + k < w) lo |= (unsigned)__ldg(row + x0 + k) << (8 * k);
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (x0 + 4 + k < w) hi |= (unsigned)__ldg(row + x0 + 4 + k) << (8 * k);
+    }
+    unsigned prev = __shfl_up_sync(0xffffffffu, hi >> 24, 1);
+    if (lane == 0) prev = (x0 > 0) ? (unsigned)__ldg(row + x0 - 1) : 0u;
+    v[0] = (int)prev;
+    v[1] = (int)(lo & 0xff); v[2] = (int)((lo >> 8) & 0xff); v[3] = (int)((lo >> 16) & 0xff); v[4] = (int)(lo >> 24);
+    v[5] = (int)(hi & 0xff); v[6] = (int)((hi >> 8) & 0xff); v[7] = (int)((hi >> 16) & 0xff);
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Pass A. grid (nchunks, nbands, nframes), 256 threads.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(kThreads)
+integral_reduce(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs, size_t image_stride, int pitch,
+                int* __restrict__ T, int* __restrict__ R, int* __restrict__ TT) {
+    __shared__ int part[8][kChunk];
+    __shared__ int wtot[8];
+    const int c = blockIdx.x, b = blockIdx.y, f = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint8_t* img = imgs + (size_t)f * image_stride;
+    const int hpad = P.nbands * kBand;
+    int acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0;
+    for (int r = warp; r < kBand; r += 8) {
+        const int y = b * kBand + r;
+        int v[8];
+        if (y < P.h) {
+            load_shifted<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane, v);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = 0;
+        }
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { s += v[k]; acc[k] += v[k]; }
+        s = warp_sum(s);
+        if (lane == 0) R[((size_t)f * hpad + y) * P.nchunks + c] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) part[warp][8 * lane + k] = acc[k];
+    __syncthreads();
+    int col = 0;
+#pragma unroll
+    for (int wq = 0; wq < 8; wq++) col += part[wq][tid];
+    T[(((size_t)f * P.nbands + b) * P.nchunks + c) * kChunk + tid] = col;
+    const int ws = warp_sum(col);
+    if (lane == 0) wtot[warp] = ws;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+#pragma unroll
+        for (int wq = 0; wq < 8; wq++) t += wtot[wq];
+        TT[((size_t)f * P.nbands + b) * P.nchunks + c] = t;
+    }
+}
+
+// Pass B. grid (nchunks, nbands, nframes), 256 threads, 32 KB static shared memory.
+template <bool ALIGNED>
+__global__ void __launch_bounds__(kThreads)
+integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs, size_t image_stride, int pitch,
+              const int* __restrict__ T, const int* __restrict__ R, const int* __restrict__ TT, int* __restrict__ Iout) {
+    __shared__ __align__(16) int tile[kBand][kChunk];
+    __shared__ int wtot[8];
+    __shared__ int s_off;
+    const int c = blockIdx.x, b = blockIdx.y, f = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = P.nbands, nc = P.nchunks;
+    const uint8_t* img = imgs + (size_t)f * image_stride;
+    const int hpad = nb * kBand;
+
+    // ---- carry row: integral at the top edge of this band, for this thread's output column
+    int colc = 0;
+    {
+        const int* Tp = T + (((size_t)f * nb) * nc + c) * kChunk + tid;
+        const size_t bstride = (size_t)nc * kChunk;
+        int bb = 0;
+        for (; bb + 4 <= b; bb += 4) {
+            const int a0 = __ldg(Tp + (size_t)bb * bstride), a1 = __ldg(Tp + (size_t)(bb + 1) * bstride);
+            const int a2 = __ldg(Tp + (size_t)(bb + 2) * bstride), a3 = __ldg(Tp + (size_t)(bb + 3) * bstride);
+            colc += (a0 + a1) + (a2 + a3);
+        }
+        for (; bb < b; bb++) colc += __ldg(Tp + (size_t)bb * bstride);
+    }
+    int off = 0;
+    if (c > 0)
+        for (int idx = tid; idx < b * c; idx += kThreads) {
+            const int bb = idx / c, cc = idx - bb * c;
+            off += __ldg(TT + ((size_t)f * nb + bb) * nc + cc);
+        }
+    // block reduce `off`, block inclusive scan of `colc`
+    off = warp_sum(off);
+    int incl = warp_incl_scan(colc, lane);
+    if (lane == 31) wtot[warp] = incl;
+    if (tid == 0) s_off = 0;
+    __syncthreads();
+    if (lane == 0 && off != 0) atomicAdd(&s_off, off);
+    int wbase = 0;
+#pragma unroll
+    for (int wq = 0; wq < 8; wq++) if (wq < warp) wbase += wtot[wq];
+    __syncthreads();
+    const int carry = s_off + wbase + incl;
+
+    // ---- row scans: warp per row, 8 pixels per lane
+    for (int r = warp; r < kBand; r += 8) {
+        const int y = b * kBand + r;
+        int v[8];
+        int rowbase = 0;
+        if (y < P.h) {
+            load_shifted<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane, v);
+            for (int cc = lane; cc < c; cc += 32) rowbase += __ldg(R + ((size_t)f * hpad + y) * nc + cc);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = 0;
+        }
+        rowbase = warp_sum(rowbase);
+#pragma unroll
+        for (int k = 1; k < 8; k++) v[k] += v[k - 1];
+        const int inc = warp_incl_scan(v[7], lane);
+        const int base = rowbase + inc - v[7];
+        int4* dst = reinterpret_cast<int4*>(&tile[r][8 * lane]);
+        dst[0] = make_int4(base + v[0], base + v[1], base + v[2], base + v[3]);
+        dst[1] = make_int4(base + v[4], base + v[5], base + v[6], base + v[7]);
+    }
+    __syncthreads();
+
+    // ---- column scan down the tile, one output column per thread, full-line row stores
+    const int X = kChunk * c + tid;
+    if (X < P.iw) {
+        int* out = Iout + (size_t)f * P.istride + P.ip /*guard row*/ + X;
+        int run = carry;
+        const int rows = min(kBand, P.h - b * kBand);
+        for (int r = 0; r < rows; r++) {
+            run += tile[r][tid];
+            out[(size_t)(b * kBand + r + 1) * P.ip] = run;
+        }
+    }
+}
+
+cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
+                            int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st) {
+    const dim3 grid(P.nchunks, P.nbands, nframes), block(kThreads);
+    const bool aligned = (pitch % 8 == 0) && (image_stride % 8 == 0) && ((uintptr_t)d_images % 8 == 0);
+    if (aligned) {
+        integral_reduce<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
+        integral_scan<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral);
+    } else {
+        integral_reduce<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
+        integral_scan<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace sb

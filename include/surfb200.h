@@ -1,0 +1,138 @@
+/* surfb200.h -- C-ABI of libsurfb200.so, the B200-native (sm_100a) SURF hot path.
+ *
+ * Drop-in boundary for the detect / describe / match path of Accustomer/CUDA-SURF. Each entry
+ * point names the reference interface it replaces (file:line under /root/reference). Plain
+ * pointers and sizes only; no C++ or torch types. All device pointers are CUDA device memory of
+ * the context's device. Functions return SB_OK (0) or a negative sb_status; sb_last_error()
+ * gives the text. A context is single-threaded; any number of contexts (one per GPU / host
+ * thread) may coexist -- there is no module-level state (the reference keeps its parameters in
+ * __constant__/__device__ symbols, surfd.cu:13-24, and is not re-entrant).
+ *
+ * There is no CPU fallback: every compute entry point fails with SB_ERR_CUDA when no sm_100
+ * device is usable.
+ */
+#ifndef SURFB200_H
+#define SURFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_VERSION 100
+
+typedef enum {
+    SB_OK = 0,
+    SB_ERR_INVALID = -1,     /* bad argument */
+    SB_ERR_CUDA = -2,        /* CUDA runtime / launch failure, or no usable device */
+    SB_ERR_UNSUPPORTED = -3, /* valid reference configuration not built yet (doubled=true) */
+    SB_ERR_NOMEM = -4
+} sb_status;
+
+/* Bit-for-bit layout of surf::SurfPoint (surf_structures.h:7-31), 48 bytes. */
+typedef struct sb_point {
+    float x, y;      /* sub-pixel position in image pixels                      */
+    float scale;     /* 1.2 * lobe/3                                            */
+    int o;           /* octave index (the reference leaves this field unset)    */
+    float strength;  /* interpolated det-of-Hessian                             */
+    int laplace;     /* sign of the Laplacian, +1 / -1                          */
+    float ori;       /* orientation (radians), 0 when upright                   */
+    float score;     /* best correlation (after sb_match)                       */
+    int match;       /* index of the best match in set 2, -1 if none            */
+    float match_x, match_y;
+    float ambiguity; /* second / best score                                     */
+} sb_point;
+
+/* Arguments of surf::Surfor::init (surf.h:27-29, surf.cpp:60-91) plus capacities. */
+typedef struct sb_params {
+    int noctaves;       /* _noctaves                                            */
+    float thresh;       /* _thresh                                              */
+    int doubled;        /* _doubled      (1 -> SB_ERR_UNSUPPORTED this round)   */
+    int init_mask_size; /* _init_mask_size (9 -> lobe 3, 5 layers per octave)   */
+    int sampling_step;  /* _sampling_step                                       */
+    int upright;        /* _upright                                             */
+    int extend;         /* _extend       (SURF-128)                             */
+    int desc_wsz;       /* _desc_wsz                                            */
+    int width, height;  /* _width, _height: frame size the context is built for */
+    int max_pts;        /* keypoint capacity per frame (SurfData.max_pts)       */
+    int batch;          /* frames per batched call (scratch capacity), >= 1     */
+    int device;         /* CUDA device ordinal                                  */
+} sb_params;
+
+/* Derived geometry (surf.cpp:374-390), for callers that size buffers. */
+typedef struct sb_info {
+    int max_scale, nfeatures;
+    int iw, ih, ipitch;        /* integral image (w+1, h+1, pitch in ints)       */
+    int sw[8], sh[8], sp[8];   /* per-octave response dims and pitch             */
+    long long resp_floats;     /* tight floats per frame: sum max_scale*sw*sh    */
+    int kernels_per_frame;     /* launches per detect+describe pass              */
+} sb_info;
+
+typedef struct sb_ctx sb_ctx;
+
+/* Surfor::Surfor + Surfor::init + the lazy allocMemory (surf.cpp:42-91, 374-415). */
+int sb_create(sb_ctx** out, const sb_params* params);
+/* Surfor::~Surfor (surf.cpp:47-57). */
+void sb_destroy(sb_ctx* ctx);
+/* Text of the last error on this context (ctx may be NULL: last sb_create error of the thread). */
+const char* sb_last_error(const sb_ctx* ctx);
+int sb_get_info(const sb_ctx* ctx, sb_info* info);
+
+/* Surfor::detectAndCompute (surf.h:36, surf.cpp:205-355). Synchronous.
+ *   d_image   device u8, row pitch `pitch` bytes, w x h must equal the context's size
+ *   d_points  device array of max_pts points (SurfData.d_data); all detector fields written
+ *   h_points  nullable host array (SurfData.h_data); gets x,y,scale,o,strength,laplace(,ori)
+ *             of the first *num_pts points, other fields untouched (surf.cpp:335-342)
+ *   d_desc_addr  in/out. NULL: no descriptors. *d_desc_addr == NULL: a device buffer of
+ *             max_pts*nfeatures floats is cudaMalloc'ed and stored there (caller cudaFree's it,
+ *             as main.cpp:275-282 does). *d_desc_addr != NULL: that buffer (>= max_pts*nfeatures
+ *             floats) is reused -- the reference allocates a new one every call and leaks the
+ *             old (surfd.cu:3264).
+ *   want_desc 0 -> detection only (the `desc` flag).                                          */
+int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w, int h, int pitch, sb_point* d_points,
+                          sb_point* h_points, int max_pts, int* num_pts, float** d_desc_addr, int want_desc);
+
+/* Surfor::match (surf.h:40, surf.cpp:418-428) -> cuFindMaxCorr (surfd.cu:3550-3566).
+ * Writes score, match, match_x, match_y, ambiguity of d_pts1[0..n1) (and h_pts1 if non-NULL).
+ * Candidates are the first n2 - n2%32 points of set 2, as in the reference (surfd.cu:2569).    */
+int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const float* d_feat1, const sb_point* d_pts2,
+             int n2, const float* d_feat2);
+
+/* Batched, asynchronous form of detectAndCompute for independent frames (the frame loop of
+ * main.cpp:239-245 without a host round trip per frame). nframes <= params.batch.
+ *   d_images  frame f at d_images + f*image_stride (bytes), row pitch `pitch`
+ *   d_points  [nframes][max_pts]; d_counts [nframes] (clamped to max_pts); d_desc nullable
+ *             [nframes][max_pts][nfeatures]
+ *   stream    cudaStream_t (NULL -> the context's stream). Returns after enqueueing.           */
+int sb_detect_batch_async(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
+                          sb_point* d_points, int* d_counts, float* d_desc, void* stream);
+/* End-to-end form with HOST buffers: H2D of the frames, the batch above, D2H of counts, points
+ * and descriptors, synchronised on return. h_images tight (pitch == width).                   */
+int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, sb_point* h_points, int* h_counts,
+                         float* h_desc);
+int sb_sync(sb_ctx* ctx);
+/* Same work as sb_detect_batch_async, synchronous, with CUDA events recorded on the launching stream
+ * at the stage boundaries: stage_ms[0..3] = integral, Hessian, NMS+refine(+clamp), orientation+describe.
+ * Measurement aid for bench.py (per-kernel roofline); not a reference interface.                */
+int sb_detect_batch_profile(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
+                            sb_point* d_points, int* d_counts, float* d_desc, void* stream, float* stage_ms);
+
+/* Stage access for parity tests (the reference exposes these stages as cuIntegral,
+ * cuCalcHessianMulti, cuDescribe in surfd.h:63,104,132). `slot` is the frame slot of the last
+ * detect call (0 for sb_detect_and_compute). Outputs are tight host arrays.                   */
+int sb_get_integral(sb_ctx* ctx, int slot, int32_t* h_out /* (h+1)*(w+1) */);
+int sb_get_response(sb_ctx* ctx, int slot, float* h_out /* sb_info.resp_floats */);
+/* (orientation if !upright) + descriptors + normalisation for caller-supplied points on the
+ * integral image held in `slot` (cuDescribe, surfd.cu:3251-3325). d_points' ori is updated.   */
+int sb_describe(sb_ctx* ctx, int slot, sb_point* d_points, int n, float* d_desc);
+
+/* Workload generator `synth_v1`: deterministic textured frame, host memory. */
+int sb_synth_frame(uint8_t* out, int w, int h, int pitch, uint64_t seed, int shift_x, int noise_amp,
+                   uint64_t noise_seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFB200_H */

@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with `pytest -m gpu`")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` on a GPU-less box would otherwise fail every test on sb_create; skip with the reason instead
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (run through gpurun)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)

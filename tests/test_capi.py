@@ -1,0 +1,99 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol include/surfb200.h
+declares, validates parameters, and FAILS LOUDLY without a GPU (no CPU fallback). No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cuda_surf_b200 as sb
+from cuda_surf_b200 import binding as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "surfb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = sb.lib()
+    names = declared_symbols()
+    assert len(names) >= 13, names
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/surfb200.h but not exported"
+
+
+def test_point_layout_is_surfpoint():
+    # surf_structures.h:7-31 -- 12 four-byte fields, 48 bytes, match fields start at `score`
+    assert B.POINT_DTYPE.itemsize == 48
+    assert B.POINT_DTYPE.fields["score"][1] == 28 and B.POINT_DTYPE.fields["ambiguity"][1] == 44
+    assert C.sizeof(B.SbParams) == 13 * 4
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_create_fails_loudly_without_gpu():
+    if _has_gpu():
+        pytest.skip("GPU present")
+    det = sb.Surfor()
+    with pytest.raises(sb.SurfError) as e:
+        det.init(4, 4.0, False, 9, 2, True, False, 4, 640, 480)
+    assert e.value.code == B.SB_ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("kw,code", [
+    (dict(doubled=True), B.SB_ERR_UNSUPPORTED),       # next row
+    (dict(noctaves=9), B.SB_ERR_INVALID),             # MAX_OCTAVE 8 (surfd.h:10)
+    (dict(init_mask_size=21), B.SB_ERR_INVALID),      # lobe 7 -> 9 layers > MAX_SCALE 8 (surfd.h:9)
+    (dict(width=16), B.SB_ERR_INVALID),
+    (dict(desc_wsz=5), B.SB_ERR_INVALID),
+    (dict(width=4000, height=3000), B.SB_ERR_INVALID),  # int32 integral would overflow
+    (dict(noctaves=8, width=64, height=64), B.SB_ERR_INVALID),
+])
+def test_parameter_validation(kw, code):
+    args = dict(noctaves=4, thresh=4.0, doubled=False, init_mask_size=9, sampling_step=2, upright=True, extend=False,
+                desc_wsz=4, width=640, height=480)
+    args.update(kw)
+    with pytest.raises(sb.SurfError) as e:
+        sb.Surfor().init(**args)
+    assert e.value.code == code, str(e.value)
+
+
+def test_null_arguments_are_rejected():
+    L = sb.lib()
+    assert L.sb_create(None, None) == B.SB_ERR_INVALID
+    assert L.sb_get_info(None, None) == B.SB_ERR_INVALID
+    assert L.sb_sync(None) == B.SB_ERR_INVALID
+    L.sb_destroy(None)  # no-op
+
+
+def test_synth_is_deterministic_and_shift_consistent():
+    a = sb.synth_frame(320, 200, 42)
+    b = sb.synth_frame(320, 200, 42)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, sb.synth_frame(320, 200, 43))
+    # a view shifted by 12 px shows the same texture (stereo pairs of BASELINE config 5)
+    c = sb.synth_frame(320, 200, 42, 12, 0, 0)
+    assert np.array_equal(a[:, 12:], c[:, :-12])
+    d = sb.synth_frame(320, 200, 42, 12, 2, 7)
+    assert np.abs(d.astype(int) - c.astype(int)).max() <= 2
+    assert 20 < a.std() < 80
+
+
+def test_product_does_not_touch_the_oracle():
+    """the product tree must not import, link or name anything under oracle/"""
+    pkg = os.path.join(ROOT, "cuda-surf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "surf_oracle" not in txt, f
+    out = os.popen(f"ldd {B.LIB_PATH}").read()
+    assert "oracle" not in out

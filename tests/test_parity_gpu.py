@@ -1,0 +1,364 @@
+"""Parity of the CUDA path (libsurfb200.so, called through the C-ABI) against
+  (1) the CPU oracle (oracle/liboracle.so),
+  (2) the unmodified reference built for sm_100a (oracle/_ref/libsurfref.so) when it is present,
+  (3) the committed golden vectors of the reference (tests/golden/*.npz).
+Bars (BASELINE.json north_star): integral bit-exact; Hessian maps within 1e-5 relative (bit-exact in
+practice); >= 99 % of keypoints within 0.1 px and 0.05 in scale, disagreements listed; descriptors
+within 1e-3 L2; match indices equal.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import ref_lib
+from helpers import describe_misses, keypoint_parity, load_golden, load_pair
+
+pytestmark = pytest.mark.gpu
+
+REF = pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref/libsurfref.so not built")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _sb():
+    import cuda_surf_b200 as sb
+    return sb
+
+
+def make_det(w, h, noctaves=4, thresh=4.0, upright=True, extend=False, max_pts=32768, batch=1):
+    sb = _sb()
+    det = sb.Surfor()
+    det.init(noctaves, thresh, False, 9, 2, upright, extend, 4, w, h, max_pts=max_pts, batch=batch)
+    return det
+
+
+def upload(img, pitch=None):
+    torch = _torch()
+    sb = _sb()
+    h, w = img.shape
+    pitch = pitch or sb.iAlignUp(w, 128)
+    buf = np.zeros((h, pitch), np.uint8)
+    buf[:, :w] = img
+    return torch.from_numpy(buf).cuda(), (w, h, pitch)
+
+
+def run_detect(det, img, max_pts=32768, desc=True, pitch=None):
+    sb = _sb()
+    d_img, whp = upload(img, pitch)
+    data = sb.initSurfData(max_pts, True, True)
+    dd = det.detectAndCompute(d_img, data, whp, desc=desc)
+    pts = data.host_points()
+    de = dd[: data.num_pts].cpu().numpy() if desc else None
+    return data, pts, de
+
+
+def assert_resp_close(got, want, what):
+    assert got.shape == want.shape, what
+    if np.array_equal(got, want):
+        return
+    denom = np.maximum(np.abs(want), 1e-3)
+    rel = np.abs(got - want) / denom
+    assert rel.max() <= 1e-5, f"{what}: max rel err {rel.max():.3e} at {np.unravel_index(rel.argmax(), rel.shape)}"
+
+
+CASES = [  # (w, h, seed, noctaves)  -- ragged sizes on purpose
+    (320, 240, 3, 3),
+    (333, 251, 4, 3),
+    (640, 480, 5000, 4),
+    (1281, 723, 11, 4),
+    (257, 131, 12, 2),
+]
+
+
+@pytest.mark.parametrize("w,h,seed,noct", CASES)
+def test_integral_and_hessian_vs_oracle(w, h, seed, noct):
+    sb = _sb()
+    img = sb.synth_frame(w, h, seed)
+    det = make_det(w, h, noct)
+    run_detect(det, img, desc=False)
+    orc = ol.Oracle(noct, 4.0, False, 9, 2, True, False, 4)
+    I = orc.integral(img)
+    got_I = det.get_integral()
+    assert np.array_equal(got_I, I), f"integral differs at {np.argwhere(got_I != I)[:5]}"
+    want = orc.hessian(I)
+    got = det.get_response()
+    for o, (g, wnt) in enumerate(zip(det.split_response(got), orc.split_resp(want, w, h))):
+        assert_resp_close(g, wnt, f"octave {o}")
+
+
+@pytest.mark.parametrize("pitch_pad", [0, 3])
+def test_integral_unaligned_pitch(pitch_pad):
+    """pitch not a multiple of 8 takes the byte-load path of the integral kernels"""
+    sb = _sb()
+    w, h = 300, 200
+    img = sb.synth_frame(w, h, 21)
+    det = make_det(w, h, 2)
+    run_detect(det, img, desc=False, pitch=w + pitch_pad)
+    assert np.array_equal(det.get_integral(), ol.Oracle(2).integral(img))
+
+
+@pytest.mark.parametrize("w,h,seed,noct", CASES[:4])
+@pytest.mark.parametrize("upright", [True, False])
+def test_keypoints_and_descriptors_vs_oracle(w, h, seed, noct, upright):
+    sb = _sb()
+    img = sb.synth_frame(w, h, seed)
+    det = make_det(w, h, noct, upright=upright)
+    data, pts, desc = run_detect(det, img)
+    orc = ol.Oracle(noct, 4.0, False, 9, 2, upright, False, 4)
+    opts, odesc = orc.detect_and_compute(img)
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(opts, pts)
+    assert abs(len(pts) - len(opts)) <= max(2, len(opts) // 100), (len(pts), len(opts))
+    assert fr >= 0.99 and fg >= 0.99, f"matched {fr:.4f}/{fg:.4f}\nmissing:\n{describe_misses(miss_r, 4.0)}"
+    assert np.array_equal(pts["laplace"][idx[ok]], opts["laplace"][ok])
+    # descriptors of matched keypoints (positions agree to float round-off, so descriptors do too)
+    exact = ok & (np.abs(pts["x"][idx] - opts["x"]) < 1e-4) & (np.abs(pts["y"][idx] - opts["y"]) < 1e-4) & \
+        (np.abs(pts["scale"][idx] - opts["scale"]) < 1e-5)
+    if not upright:
+        dori = np.abs(np.angle(np.exp(1j * (pts["ori"][idx] - opts["ori"]))))
+        assert np.median(dori[ok]) < 1e-4
+        exact &= dori < 1e-5
+    assert exact.sum() >= 0.9 * ok.sum()
+    l2 = np.linalg.norm(desc[idx[exact]] - odesc[exact], axis=1)
+    assert l2.max() <= 1e-3, f"descriptor L2 max {l2.max():.3e}"
+
+
+def test_describe_given_points_matches_oracle_exact_inputs():
+    """same keypoints in, descriptors out: isolates the descriptor kernel from detection"""
+    torch = _torch()
+    sb = _sb()
+    w, h = 640, 480
+    img = sb.synth_frame(w, h, 5000)
+    for upright, extend in [(True, False), (False, False), (True, True)]:
+        det = make_det(w, h, 4, upright=upright, extend=extend)
+        run_detect(det, img, desc=False)
+        orc = ol.Oracle(4, 4.0, False, 9, 2, upright, extend, 4)
+        I = orc.integral(img)
+        opts = orc.keypoints(I, orc.hessian(I))
+        if not upright:
+            opts = orc.orientation(I, opts)
+        want = orc.describe(I, opts)
+        d_pts = torch.from_numpy(opts.view(np.uint8).copy()).cuda()
+        d_desc = torch.zeros((len(opts), det.nfeatures), dtype=torch.float32, device="cuda")
+        det.describe(d_pts, len(opts), d_desc)
+        got = d_desc.cpu().numpy()
+        if not upright:
+            gori = d_pts.cpu().numpy().view(sb.POINT_DTYPE)["ori"]
+            dori = np.abs(np.angle(np.exp(1j * (gori - opts["ori"]))))
+            assert np.nanmax(dori) < 1e-3, f"orientation differs by {np.nanmax(dori)}"
+        l2 = np.linalg.norm(got - want, axis=1)
+        bad = np.isnan(l2)
+        assert not bad.any()
+        # rotated descriptors inherit the orientation's round-off through sin/cos
+        assert l2.max() <= (1e-3 if upright else 5e-3), f"upright={upright} extend={extend}: L2 max {l2.max():.3e}"
+
+
+@REF
+@pytest.mark.parametrize("which", ["left", "right"])
+def test_bundled_pair_vs_reference(which):
+    """config 1 of BASELINE.md: main.cpp defaults on the reference's own stereo pair"""
+    left, right = load_pair()
+    img = left if which == "left" else right
+    h, w = img.shape
+    ref = ref_lib.Reference(w, h, 4, 4.0, False, 9, 2, True, False, 4)
+    rpts, rdesc = ref.detect(img, max_pts=32768)
+    rI, rlayers, _ = ref.stages(img)
+    ref.close()
+    det = make_det(w, h, 4)
+    data, pts, desc = run_detect(det, img)
+    assert np.array_equal(det.get_integral(), rI)
+    for o, (g, wnt) in enumerate(zip(det.split_response(det.get_response()), rlayers)):
+        assert_resp_close(g, wnt, f"octave {o}")
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(rpts, pts)
+    assert fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\nreference-only:\n{describe_misses(miss_r, 4.0)}\nours-only:\n{describe_misses(miss_g, 4.0)}"
+    assert np.array_equal(pts["laplace"][idx[ok]], rpts["laplace"][ok])
+    l2 = np.linalg.norm(desc[idx[ok]] - rdesc[ok], axis=1)
+    assert (l2 <= 1e-3).mean() >= 0.99, f"descriptor L2: max {l2.max():.3e}, frac ok {(l2 <= 1e-3).mean():.4f}"
+
+
+@REF
+@pytest.mark.parametrize("upright,extend", [(True, False), (False, False), (True, True)])
+def test_describe_vs_reference_same_points(upright, extend):
+    torch = _torch()
+    sb = _sb()
+    w, h = 640, 480
+    img = sb.synth_frame(w, h, 5000)
+    ref = ref_lib.Reference(w, h, 4, 4.0, False, 9, 2, upright, extend, 4)
+    rpts, rdesc = ref.detect(img)
+    ref.close()
+    det = make_det(w, h, 4, upright=upright, extend=extend)
+    run_detect(det, img, desc=False)
+    d_pts = torch.from_numpy(rpts.view(np.uint8).copy()).cuda()
+    d_desc = torch.zeros((len(rpts), det.nfeatures), dtype=torch.float32, device="cuda")
+    det.describe(d_pts, len(rpts), d_desc)
+    got = d_desc.cpu().numpy()
+    if not upright:
+        gori = d_pts.cpu().numpy().view(sb.POINT_DTYPE)["ori"]
+        dori = np.abs(np.angle(np.exp(1j * (gori - rpts["ori"]))))
+        assert np.nanmax(dori) < 1e-3, f"orientation differs by {np.nanmax(dori)}"
+    l2 = np.linalg.norm(got - rdesc, axis=1)
+    assert np.isfinite(l2).all()
+    assert l2.max() <= (1e-3 if upright else 5e-3), f"L2 max {l2.max():.3e}"
+
+
+@REF
+def test_match_vs_reference():
+    sb = _sb()
+    torch = _torch()
+    w, h = 640, 480
+    sl = sb.synth_frame(w, h, 5000)
+    sr = sb.synth_frame(w, h, 5000, 12, 2, 5000 ^ 0xA5A5)
+    det = make_det(w, h, 4)
+    d1, p1, f1 = run_detect(det, sl)
+    d1_desc = torch.from_numpy(f1).cuda()
+    d2, p2, f2 = run_detect(det, sr)
+    d2_desc = torch.from_numpy(f2).cuda()
+    det.match(d1, d2, d1_desc, d2_desc)
+    got = d1.host_points()
+    ref = ref_lib.Reference(w, h, 4)
+    want = ref.match(p1, f1, p2, f2)
+    ref.close()
+    assert np.array_equal(got["match"], want["match"])
+    assert np.array_equal(got["score"], want["score"])
+    assert np.allclose(got["ambiguity"], want["ambiguity"], rtol=0, atol=1e-6)
+    assert np.array_equal(got["match_x"], want["match_x"]) and np.array_equal(got["match_y"], want["match_y"])
+    # host copy of the five match fields (surf.cpp:421-425)
+    assert np.array_equal(d1.h_data["match"][: d1.num_pts], got["match"])
+
+
+def test_match_vs_oracle_and_tail_rule():
+    sb = _sb()
+    torch = _torch()
+    rng = np.random.default_rng(5)
+    for n1, n2 in [(100, 95), (33, 64), (257, 1000), (5, 31)]:
+        f1 = rng.standard_normal((n1, 64)).astype(np.float32)
+        f2 = rng.standard_normal((n2, 64)).astype(np.float32)
+        f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+        f2 /= np.linalg.norm(f2, axis=1, keepdims=True)
+        p1 = np.zeros(n1, ol.POINT_DTYPE)
+        p2 = np.zeros(n2, ol.POINT_DTYPE)
+        p2["x"] = rng.random(n2).astype(np.float32)
+        p2["y"] = rng.random(n2).astype(np.float32)
+        want = ol.match(p1, f1, p2, f2)
+        det = make_det(64, 64, 1, max_pts=2048)
+        a = sb.initSurfData(2048)
+        b = sb.initSurfData(2048)
+        a.num_pts, b.num_pts = n1, n2
+        a.d_data[: n1 * 48] = torch.from_numpy(p1.view(np.uint8)).cuda()
+        b.d_data[: n2 * 48] = torch.from_numpy(p2.view(np.uint8)).cuda()
+        det.match(a, b, torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda())
+        got = a.host_points()
+        assert np.array_equal(got["match"], want["match"]), (n1, n2)
+        assert (got["match"] < n2 - n2 % 32).all()  # the last n2 % 32 descriptors are never candidates
+        assert np.array_equal(got["score"], want["score"])
+        assert np.allclose(got["ambiguity"], want["ambiguity"], atol=1e-6)
+
+
+def test_golden_pair_counts():
+    """committed golden vectors of the reference (skips until they exist)"""
+    g = load_golden("pair_left_upright")
+    if g is None:
+        pytest.skip("tests/golden/pair_left_upright.npz not generated yet")
+    left, _ = load_pair()
+    det = make_det(1280, 960, 4)
+    data, pts, desc = run_detect(det, left)
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(g["pts"], pts)
+    assert fr >= 0.99 and fg >= 0.99
+
+
+# ------------------------------------------------------------------ properties at full size
+
+@pytest.mark.parametrize("w,h,seed", [(1920, 1080, 1), (3840, 2160, 2)])
+def test_full_size_properties(w, h, seed):
+    """BASELINE configs 2 and 3: checks that do not need the (slow) oracle beyond the integral"""
+    sb = _sb()
+    img = sb.synth_frame(w, h, seed)
+    det = make_det(w, h, 5, max_pts=65536)
+    data, pts, desc = run_detect(det, img, max_pts=65536)
+    I = det.get_integral()
+    assert I[-1, -1] == int(img.astype(np.int64).sum())
+    assert np.array_equal(I, ol.Oracle(5).integral(img))
+    assert not (I[0, :].any() or I[:, 0].any())
+    # idempotence: the same frame again gives the same set (order may differ)
+    data2, pts2, desc2 = run_detect(det, img, max_pts=65536)
+    assert len(pts) == len(pts2)
+    k1 = np.sort(pts, order=["x", "y", "scale"])
+    k2 = np.sort(pts2, order=["x", "y", "scale"])
+    assert np.array_equal(k1["x"], k2["x"]) and np.array_equal(k1["strength"], k2["strength"])
+    # descriptors are unit vectors, keypoints inside the frame, strengths above threshold
+    nrm = np.linalg.norm(desc, axis=1)
+    assert np.allclose(nrm, 1.0, atol=1e-5)
+    assert (pts["strength"] >= 4.0).all() and (pts["x"] > 0).all() and (pts["x"] < w).all() and (pts["y"] < h).all()
+    assert 1.5 < len(pts) / (w * h / 1000.0) < 3.5, len(pts)  # synth_v1 density
+    if w == 1920:
+        opts, _ = ol.Oracle(5, 4.0, False, 9, 2, True, False, 4).detect_and_compute(img, desc=False)
+        fr, fg, *_ = keypoint_parity(opts, pts)
+        assert fr >= 0.99 and fg >= 0.99
+
+
+def test_batch_equals_single_and_host_path():
+    sb = _sb()
+    torch = _torch()
+    w, h, nb = 640, 480, 5
+    frames = np.stack([sb.synth_frame(w, h, 100 + i) for i in range(nb)])
+    det = make_det(w, h, 4, max_pts=4096, batch=nb)
+    pitch = sb.iAlignUp(w, 128)
+    buf = np.zeros((nb, h, pitch), np.uint8)
+    buf[:, :, :w] = frames
+    d_imgs = torch.from_numpy(buf).cuda()
+    pts = torch.zeros((nb, 4096 * 48), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    desc = torch.zeros((nb, 4096, 64), dtype=torch.float32, device="cuda")
+    det.detect_batch(d_imgs, pitch, pts, cnt, desc)
+    torch.cuda.synchronize()
+    counts = cnt.cpu().numpy()
+    # host-buffer end-to-end entry point
+    hp = np.zeros((nb, 4096), sb.POINT_DTYPE)
+    hc = np.zeros(nb, np.int32)
+    hd = np.zeros((nb, 4096, 64), np.float32)
+    det.detect_batch_host(frames, hp, hc, hd)
+    assert np.array_equal(hc, counts)
+    single = make_det(w, h, 4, max_pts=4096)
+    for f in range(nb):
+        data, spts, sdesc = run_detect(single, frames[f], max_pts=4096)
+        assert data.num_pts == counts[f]
+        bp = pts[f].cpu().numpy().view(sb.POINT_DTYPE)[: counts[f]]
+        bd = desc[f, : counts[f]].cpu().numpy()
+        for got_p, got_d in ((bp, bd), (hp[f, : hc[f]], hd[f, : hc[f]])):
+            o1 = np.argsort(got_p, order=["x", "y", "scale"])
+            o2 = np.argsort(spts, order=["x", "y", "scale"])
+            assert np.array_equal(got_p["x"][o1], spts["x"][o2])
+            assert np.array_equal(got_d[o1], sdesc[o2])
+
+
+def test_edge_cases():
+    sb = _sb()
+    # blank frame: no keypoints, nothing crashes
+    det = make_det(128, 96, 2, max_pts=64)
+    data, pts, desc = run_detect(det, np.full((96, 128), 77, np.uint8), max_pts=64)
+    assert data.num_pts == 0
+    # keypoint cap: count clamps to max_pts, nothing is written past the buffer
+    img = sb.synth_frame(640, 480, 9)
+    det = make_det(640, 480, 4, max_pts=100)
+    torch = _torch()
+    d_img, whp = upload(img)
+    data = sb.initSurfData(100)
+    guard = torch.full((4800 + 4800,), 0xAB, dtype=torch.uint8, device="cuda")
+    data.d_data = guard[:4800]
+    det.detectAndCompute(d_img, data, whp)
+    assert data.num_pts == 100
+    assert (guard[4800:] == 0xAB).all()
+    # smallest frame the library accepts; 8 octaves on a small frame is refused, not crashed
+    det = make_det(32, 32, 1, max_pts=16)
+    run_detect(det, sb.synth_frame(32, 32, 1), max_pts=16)
+    with pytest.raises(sb.SurfError):
+        make_det(64, 64, 8)
+    # wrong frame size for the context is an error (the reference would read uninitialised scratch)
+    det = make_det(128, 96, 2, max_pts=64)
+    d_img, whp = upload(sb.synth_frame(100, 96, 1))
+    with pytest.raises(sb.SurfError):
+        det.detectAndCompute(d_img, sb.initSurfData(64), whp)
