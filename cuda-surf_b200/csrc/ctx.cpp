@@ -262,7 +262,7 @@ extern "C" int sb_detect_batch_profile(sb_ctx* ctx, const uint8_t* d_images, siz
     if (!d_images || !d_points || !d_counts || !stage_ms || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->P.w)
         return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_profile: bad argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     cudaEvent_t ev[5];
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&ev[i]));
     int rc = enqueue_frames(ctx, d_images, image_stride, pitch, nframes, d_points, d_counts, d_desc, st, ev);
@@ -281,8 +281,8 @@ extern "C" int sb_detect_batch_async(sb_ctx* ctx, const uint8_t* d_images, size_
     if (!d_images || !d_points || !d_counts || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->P.w)
         return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_async: bad argument (nframes must be 1..batch, pitch >= width)");
     CU(cudaSetDevice(ctx->device));
-    return enqueue_frames(ctx, d_images, image_stride, pitch, nframes, d_points, d_counts, d_desc,
-                          stream ? (cudaStream_t)stream : ctx->stream);
+    // `stream` is used literally: NULL is the CUDA default stream, as for any CUDA API
+    return enqueue_frames(ctx, d_images, image_stride, pitch, nframes, d_points, d_counts, d_desc, (cudaStream_t)stream);
 }
 
 extern "C" int sb_sync(sb_ctx* ctx) {

@@ -105,7 +105,8 @@ int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const floa
  *   d_images  frame f at d_images + f*image_stride (bytes), row pitch `pitch`
  *   d_points  [nframes][max_pts]; d_counts [nframes] (clamped to max_pts); d_desc nullable
  *             [nframes][max_pts][nfeatures]
- *   stream    cudaStream_t (NULL -> the context's stream). Returns after enqueueing.           */
+ *   stream    cudaStream_t, used as given (NULL is the CUDA default stream). Returns after
+ *             enqueueing; results are ordered on that stream.                                 */
 int sb_detect_batch_async(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
                           sb_point* d_points, int* d_counts, float* d_desc, void* stream);
 /* End-to-end form with HOST buffers: H2D of the frames, the batch above, D2H of counts, points
