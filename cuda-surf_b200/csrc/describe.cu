@@ -16,6 +16,8 @@
 //   * descriptors leave the SM once, as 128-byte coalesced stores.
 // Arithmetic (rounding modes, FMA placement, IEEE division, __sinf/__cosf) follows the reference
 // so that descriptors agree to float round-off.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sb {
@@ -321,22 +323,250 @@ describe_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, 
     }
 }
 
+
+// ------------------------------------------------------------------ upright descriptor, v2
+//
+// Upright sampling is separable: rpos depends only on the lattice row, cpos only on the column.
+// A lane therefore OWNS a lattice column (its cpos, cell column ci, bilinear weights and the four
+// integral-image column offsets are computed once per pass) and sweeps the rows; the per-row
+// quantities come from a small per-keypoint table built once by the whole warp. Because the cell
+// row ri only grows along the sweep, the contributions to cell rows ri / ri+1 live in registers
+// and are flushed (x the column weights) into the lane's private descriptor copy only when ri
+// advances: ~10 shared-memory updates per column instead of 8 per sample. The two half-warps take
+// even / odd lattice rows, 16 columns per pass, so 23..45-wide lattices keep 70-97 % of the lanes
+// busy. 12 integral loads per sample (the reference's two Haar boxes share four corners).
+struct __align__(16) RowEntry { float rpos, rfrac; int ri, rowoff; };
+constexpr int kRowTab = 96;
+constexpr int kRowInvalid = -100;  // 'no current cell row' marker of the sweep
+
+template <int O>
+__device__ __forceinline__ void emit_row(float* __restrict__ h, int lane, int W, int k, int ci, float cfrac1, float cfrac,
+                                         const float (&v)[O]) {
+    if (k < 0 || k >= W) return;
+    if (ci >= 0) {
+        float* e = h + ((k * W + ci) * O) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < O; b++) e[b * 32] += __fmul_rn(v[b], cfrac1);
+    }
+    if (ci + 1 < W) {
+        float* e = h + ((k * W + ci + 1) * O) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < O; b++) e[b * 32] += __fmul_rn(v[b], cfrac);
+    }
+}
+
+template <int O>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
+                        long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
+                        long long desc_stride) {
+    extern __shared__ __align__(16) float smem[];
+    const int NF = P.nfeatures, W = P.desc_wsz;
+    const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // layout: [4 warps][NF*32] private descriptor copies | [4 warps][kRowTab] row tables | lut2[40]
+    RowEntry* rowT = reinterpret_cast<RowEntry*>(smem + kWarpsPerCta * NF * 32) + warp * kRowTab;
+    float* s_lut2 = smem + kWarpsPerCta * NF * 32 + kWarpsPerCta * kRowTab * 4;
+    for (int t = threadIdx.x; t < 40; t += blockDim.x) s_lut2[t] = P.lut2[t];
+    __syncthreads();
+    float* h = smem + warp * NF * 32;
+    const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
+    const int ip = P.ip;
+    const int* I = Ibase + (size_t)f * P.istride + ip;
+    const sb_point* pts = points + (size_t)f * pts_stride;
+    float* dout = desc + (size_t)f * desc_stride;
+    const float fW = __int2float_rn(W);
+    const int half = lane >> 4, jl = lane & 15;
+
+    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
+        for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
+        const float x = pts[pi].x, y = pts[pi].y;
+        const float sc = __fmul_rn(1.65f, pts[pi].scale);
+        const int step = max(__float2int_rn(__fmul_rn(sc, 0.5f)), 1);
+        const int ixc = __float2int_rn(x), iyc = __float2int_rn(y);
+        const float fx = __fsub_rn(x, __int2float_rn(ixc)), fy = __fsub_rn(y, __int2float_rn(iyc));
+        const float spacing = __fmul_rn(sc, __int2float_rn(P.mag_factor));
+        const int S = __float2int_rz(sc);
+        const float wofs = __fmaf_rn(fW, 0.5f, -0.5f);
+        const int R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(spacing, __int2float_rn(W + 1)), 0.5f), __int2float_rn(step)));
+        const int side = min(2 * R + 1, kRowTab);
+        // per-row table (same IEEE operations as the reference's per-sample arithmetic). Valid rows
+        // (inside the descriptor window and the image) form one contiguous range [row_lo, row_hi).
+        int row_lo = side, row_hi = 0;
+        for (int i0 = 0; i0 < side; i0 += 32) {
+            const int ii = i0 + lane;
+            const int i = ii - R;
+            const float rpos = __fdiv_rn(__fsub_rn(__int2float_rn(step * i), fy), spacing);
+            const float rx = __fadd_rn(rpos, wofs);
+            const int r = iyc + i * step;
+            const bool ok = ii < side && rx > -1.f && rx < fW && r >= 1 + S && r < P.ih - 1 - S;
+            const int ri = __float2int_rz(rx >= 0.f ? rx : __fsub_rn(rx, 1.f));
+            if (ii < side) {
+                RowEntry t;
+                t.rpos = rpos; t.rfrac = __fsub_rn(rx, __int2float_rn(ri)); t.ri = ri; t.rowoff = r * ip;
+                rowT[ii] = t;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m) {
+                row_lo = min(row_lo, i0 + __ffs(m) - 1);
+                row_hi = max(row_hi, i0 + 32 - __clz(m));
+            }
+        }
+        __syncwarp();
+        const int sip = S * ip, sip1 = sip + ip;
+        for (int p0 = 0; p0 < side; p0 += 16) {
+            const int jj = p0 + jl;
+            const int j = jj - R;
+            const float cpos = __fdiv_rn(__fsub_rn(__int2float_rn(step * j), fx), spacing);
+            const float cx = __fadd_rn(cpos, wofs);
+            const int c = ixc + j * step;
+            const bool colok = jj < side && cx > -1.f && cx < fW && c >= 1 + S && c < P.iw - 1 - S;
+            if (colok) {
+                const int ci = __float2int_rz(cx >= 0.f ? cx : __fsub_rn(cx, 1.f));
+                const float cfrac = __fsub_rn(cx, __int2float_rn(ci)), cfrac1 = __fsub_rn(1.f, cfrac);
+                const float cpos2 = __fmul_rn(cpos, cpos);
+                // Column base pointers, made opaque so every gather is ONE IMAD.WIDE (row offset * 4 + base)
+                // instead of a 64-bit add chain per load.
+                const int* pA = I + (c - S);
+                const int* pB = I + c;
+                const int* pD = I + (c + S + 1);
+                asm volatile("" : "+l"(pA), "+l"(pB), "+l"(pD));
+                // Register accumulators for cell rows `cur` (lo) and `cur`+1 (hi): signed sum and sum of
+                // magnitudes of dx and dy; the reference's split by sign is (S -/+ A)/2 at flush time.
+                float sl[4], sh[4];
+#pragma unroll
+                for (int b = 0; b < 4; b++) { sl[b] = 0.f; sh[b] = 0.f; }
+                float xl[4], xh[4];  // SURF-128 only: the same sums restricted to samples with dy<0 / dx<0
+#pragma unroll
+                for (int b = 0; b < 4; b++) { xl[b] = 0.f; xh[b] = 0.f; }
+                int cur = kRowInvalid;
+                auto flush = [&](int k, const float (&sv)[4], const float (&xv)[4]) {
+                    float v[O];
+                    if (O == 4) {
+                        // bins: dx<0, dx>=0, dy<0, dy>=0 (addUprightSample, surfd.cu:1308)
+                        v[0] = 0.5f * (sv[0] - sv[1]); v[1] = 0.5f * (sv[0] + sv[1]);
+                        v[2] = 0.5f * (sv[2] - sv[3]); v[3] = 0.5f * (sv[2] + sv[3]);
+                    } else {
+                        // SURF-128 (surfd.cu:1312-1313): dx,|dx| split by sign of dy; dy,|dy| split by sign of dx
+                        v[0] = xv[0]; v[1] = sv[0] - xv[0]; v[2] = xv[1]; v[3] = sv[1] - xv[1];
+                        v[4] = xv[2]; v[5] = sv[2] - xv[2]; v[6] = xv[3]; v[7] = sv[3] - xv[3];
+                    }
+                    emit_row<O>(h, lane, W, k, ci, cfrac1, cfrac, v);
+                };
+                // The 12 gathers of a sample: rows r-S (m), r (z), r+1 (u), r+S+1 (q); columns c-S (A), c (B),
+                // c+1 (C), c+S+1 (D). Software-pipelined: the gathers of this lane's NEXT row are issued before
+                // the current row is consumed, so a warp always has 12 loads in flight (the loop is latency-bound).
+                auto gather = [&](int rowoff, int (&g)[12]) {
+                    const int om = rowoff - sip, o1 = rowoff + ip, op = rowoff + sip1;
+                    g[0] = __ldg(pA + om); g[1] = __ldg(pB + om); g[2] = __ldg(pB + om + 1); g[3] = __ldg(pD + om);
+                    g[4] = __ldg(pA + rowoff); g[5] = __ldg(pD + rowoff);
+                    g[6] = __ldg(pA + o1); g[7] = __ldg(pD + o1);
+                    g[8] = __ldg(pA + op); g[9] = __ldg(pB + op); g[10] = __ldg(pB + op + 1); g[11] = __ldg(pD + op);
+                };
+                int ii = row_lo + half;
+                RowEntry t;
+                int g[12];
+                if (ii < row_hi) { t = rowT[ii]; gather(t.rowoff, g); }
+                while (ii < row_hi) {
+                    const int in = ii + 2;
+                    RowEntry tn = t;
+                    int gn[12];
+                    if (in < row_hi) { tn = rowT[in]; gather(tn.rowoff, gn); }
+                    if (t.ri != cur) {
+                        if (cur != kRowInvalid) {
+                            flush(cur, sl, xl);
+                            if (t.ri == cur + 1) {
+#pragma unroll
+                                for (int b = 0; b < 4; b++) { sl[b] = sh[b]; sh[b] = 0.f; xl[b] = xh[b]; xh[b] = 0.f; }
+                            } else {
+                                flush(cur + 1, sh, xh);
+#pragma unroll
+                                for (int b = 0; b < 4; b++) { sl[b] = 0.f; sh[b] = 0.f; xl[b] = 0.f; xh[b] = 0.f; }
+                            }
+                        }
+                        cur = t.ri;
+                    }
+                    const float weight = s_lut2[__float2int_rz(__fmaf_rn(t.rpos, t.rpos, cpos2))];
+                    // haar_x = box(c..c+S, r-S..r+S) - box(c-S..c, r-S..r+S); haar_y = box(c-S..c+S, r-S..r) - box(.., r..r+S)
+                    const int wx = (g[11] + g[1] - g[3] - g[9]) - (g[10] + g[0] - g[2] - g[8]);
+                    const int wy = (g[7] + g[0] - g[3] - g[6]) - (g[11] + g[4] - g[5] - g[8]);
+                    const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(wx)), kR255);
+                    const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(wy)), kR255);
+                    const float w1 = t.rfrac, w0 = __fsub_rn(1.f, w1);
+                    sl[0] = __fmaf_rn(a, w0, sl[0]); sl[1] = __fmaf_rn(fabsf(a), w0, sl[1]);
+                    sl[2] = __fmaf_rn(b, w0, sl[2]); sl[3] = __fmaf_rn(fabsf(b), w0, sl[3]);
+                    sh[0] = __fmaf_rn(a, w1, sh[0]); sh[1] = __fmaf_rn(fabsf(a), w1, sh[1]);
+                    sh[2] = __fmaf_rn(b, w1, sh[2]); sh[3] = __fmaf_rn(fabsf(b), w1, sh[3]);
+                    if (O == 8) {
+                        // the part of each sum with (dy<0) for the dx-sums, (dx<0) for the dy-sums
+                        const float an = (b < 0.f) ? a : 0.f, bn = (a < 0.f) ? b : 0.f;
+                        xl[0] = __fmaf_rn(an, w0, xl[0]); xl[1] = __fmaf_rn(fabsf(an), w0, xl[1]);
+                        xl[2] = __fmaf_rn(bn, w0, xl[2]); xl[3] = __fmaf_rn(fabsf(bn), w0, xl[3]);
+                        xh[0] = __fmaf_rn(an, w1, xh[0]); xh[1] = __fmaf_rn(fabsf(an), w1, xh[1]);
+                        xh[2] = __fmaf_rn(bn, w1, xh[2]); xh[3] = __fmaf_rn(fabsf(bn), w1, xh[3]);
+                    }
+                    t = tn;
+#pragma unroll
+                    for (int k = 0; k < 12; k++) g[k] = gn[k];
+                    ii = in;
+                }
+                if (cur != kRowInvalid) {
+                    flush(cur, sl, xl);
+                    flush(cur + 1, sh, xh);
+                }
+            }
+        }
+        __syncwarp();
+        // reduce the 32 private copies (rotated read: bank == (lane + k) % 32), normalise, store
+        float v[4];
+        float sq = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = lane + 32 * u;
+            float acc = 0.f;
+            if (e < NF) {
+                for (int k = 0; k < 32; k++) acc += h[e * 32 + ((lane + k) & 31)];
+            }
+            v[u] = acc;
+            sq = __fmaf_rn(acc, acc, sq);
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
+        const float inv = __fdiv_rn(1.f, __fsqrt_rn(sq));
+        float* d = dout + (size_t)pi * NF;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = lane + 32 * u;
+            if (e < NF) d[e] = __fmul_rn(v[u], inv);
+        }
+        __syncwarp();
+    }
+}
+
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
                             cudaStream_t st) {
     const int maxn = fixed_count >= 0 ? fixed_count : P.max_pts;
     if (maxn <= 0 || nframes <= 0) return cudaSuccess;
     const int need = (maxn + kWarpsPerCta - 1) / kWarpsPerCta;
-    int ctas = (sm_count * 8 + nframes - 1) / nframes;
-    if (ctas < 32) ctas = 32;
+    // blockIdx.x runs fastest, so ~2 CTAs per SM per frame keeps only a few frames' integral images
+    // live at a time (L2-resident) while still covering the machine for a single frame
+    int ctas = sm_count * 2;
+    if (const char* e = getenv("SB_DESC_CTAS")) ctas = atoi(e);  // tuning knob (experiments only)
+    if (ctas < 1) ctas = 1;
     if (ctas > need) ctas = need;
     const dim3 grid(ctas, nframes), block(kWarpsPerCta * 32);
     if (!P.upright) orient_kernel<<<grid, block, 0, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count);
-    const size_t smem = ((size_t)kWarpsPerCta * P.nfeatures * 32 + 40) * sizeof(float);
     if (P.upright) {
-        cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        describe_kernel<true><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+        const size_t smem = ((size_t)kWarpsPerCta * P.nfeatures * 32 + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
+        if (P.orient_size == 4) {
+            cudaFuncSetAttribute(describe_upright_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            describe_upright_kernel<4><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+        } else {
+            cudaFuncSetAttribute(describe_upright_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            describe_upright_kernel<8><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+        }
     } else {
+        const size_t smem = ((size_t)kWarpsPerCta * P.nfeatures * 32 + 40) * sizeof(float);
         cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         describe_kernel<false><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
     }
