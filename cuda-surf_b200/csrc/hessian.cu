@@ -64,9 +64,9 @@ __device__ __forceinline__ float hessian_response(const int* __restrict__ I, int
 }
 
 __global__ void __launch_bounds__(256)
-hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase) {
+hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int first_tile) {
     const int f = blockIdx.y;
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x + first_tile;
     int o = 0;
     while (o + 1 < P.noctaves && tile >= P.oct[o + 1].hess_tile0) o++;
     const OctaveP& q = P.oct[o];
@@ -98,9 +98,119 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, f
     }
 }
 
+
+// ------------------------------------------------------------------ octave 0 from shared memory
+//
+// Octave 0 holds 84 % of all response samples and its filters are small (9..33 px), so a tile of
+// outputs can share one staged patch of the integral image. The gather kernel above is bound by
+// the L1 data stage: neighbouring outputs are 2 px apart, so a warp's 4-byte gathers use half of
+// every 32-byte sector (ncu: 77 % l1tex throughput, 10 sectors per request). Here a CTA stages the
+// 96x64 patch under a 32x16 output tile once, DE-INTERLEAVED by row/column parity into four planes,
+// so the 32 lanes of a warp read 32 consecutive words for every corner: one conflict-free
+// shared-memory wavefront per gather instead of 2.5 L1 cycles, and every corner address is
+// (thread base + compile-time constant) because the lobe is a template parameter.
+// Only for the reference's default geometry (sampling 2, lobes 3,5,7,9,11); anything else takes the
+// generic kernel.
+constexpr int kTW = 32, kTH = 16;            // outputs per tile
+constexpr int kPW = 96, kPH = 64;            // staged patch (integral elements)
+constexpr int kQW = kPW / 2, kQH = kPH / 2;  // plane dims
+constexpr int kPlane = kQW * kQH;            // 1536 words
+constexpr int kHalo = 16;                    // patch origin = 2*tile origin - kHalo
+
+// word offset of patch element (cy + dy, cx + dx) relative to the thread base (ly*kQW + lx)
+__host__ __device__ constexpr int corner_off(int dx, int dy) {
+    return (((dy + kHalo) & 1) * 2 + ((dx + kHalo) & 1)) * kPlane + ((dy + kHalo) >> 1) * kQW + ((dx + kHalo) >> 1);
+}
+
+template <int L>
+__device__ __forceinline__ float response_smem(const int* __restrict__ b, float norm) {
+    constexpr int x2 = L / 2, x3 = 2 * x2, x4 = 3 * x2;
+#define C_(dx, dy) b[corner_off(dx, dy)]
+    // same corners as hessian_response(): rows/cols are those of getSum (surfd.cu:334-343)
+    const int wide = C_(L + x2 + 1, x3 + 1) + C_(-L - x2, -x3) - C_(L + x2 + 1, -x3) - C_(-L - x2, x3 + 1);
+    const int midx = C_(x2 + 1, x3 + 1) + C_(-x2, -x3) - C_(x2 + 1, -x3) - C_(-x2, x3 + 1);
+    const int dxx = wide - 3 * midx;
+    const int tall = C_(x3 + 1, L + x2 + 1) + C_(-x3, -L - x2) - C_(x3 + 1, -L - x2) - C_(-x3, L + x2 + 1);
+    const int midy = C_(x3 + 1, x2 + 1) + C_(-x3, -x2) - C_(x3 + 1, -x2) - C_(-x3, x2 + 1);
+    const int dyy = tall - 3 * midy;
+    const int tr = C_(x4 + 1, 1) + C_(0, -x4) - C_(x4 + 1, -x4) - C_(0, 1);
+    const int bl = C_(1, x4 + 1) + C_(-x4, 0) - C_(1, 0) - C_(-x4, x4 + 1);
+    const int br = C_(x4 + 1, x4 + 1) + C_(0, 0) - C_(x4 + 1, 0) - C_(0, x4 + 1);
+    const int tl = C_(1, 1) + C_(-x4, -x4) - C_(1, -x4) - C_(-x4, 1);
+    const int dxy = tr + bl - br - tl;
+#undef C_
+    const float fxy = __fmul_rn(0.6f, __int2float_rn(dxy));
+    const float t = __fmul_rn(fxy, fxy);
+    float det = __fmaf_rn(__int2float_rn(dxx), __int2float_rn(dyy), -t);
+    constexpr float r255 = 0.003921568627f;
+    constexpr float rr = r255 * r255;
+    det = __fmul_rn(det, rr);
+    return __fmul_rn(det, norm);
+}
+
+template <int L, int LAYER>
+__device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict__ b, float* __restrict__ Rf, int ix, int iy) {
+    const OctaveP& q = P.oct[0];
+    const int bd = q.b1[LAYER];
+    if (ix < bd || ix >= q.sw - bd || iy < bd || iy >= q.sh - bd) return;
+    const float v = response_smem<L>(b, q.norm[LAYER]);
+    Rf[q.resp_off + (size_t)LAYER * q.osz + (size_t)iy * q.sp + ix] = v;
+    // layers 2 and 4 are what halfImage copies into layers 0 and 1 of octave 1 (surf.cpp:250-258)
+    if ((LAYER == 2 || LAYER == 4) && P.noctaves > 1 && ((ix | iy) & 1) == 0) {
+        const OctaveP& n = P.oct[1];
+        const int x = ix >> 1, y = iy >> 1;
+        if (x < n.sw && y < n.sh) Rf[n.resp_off + (size_t)(LAYER == 2 ? 0 : 1) * n.osz + (size_t)y * n.sp + x] = v;
+    }
+}
+
+// grid (tiles_x * tiles_y, nframes), 256 threads, 24 KB static shared memory
+__global__ void __launch_bounds__(256)
+hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int tiles_x) {
+    __shared__ __align__(16) int patch[4 * kPlane];
+    const int f = blockIdx.y;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int* I = Ibase + (size_t)f * P.istride + P.ip;
+    const int X0 = 2 * kTW * tx - kHalo, Y0 = 2 * kTH * ty - kHalo;
+    // stage: 64 rows x 24 int4; (x0,x2) go to the even-column plane, (x1,x3) to the odd one
+    for (int t = threadIdx.x; t < kPH * (kPW / 4); t += 256) {
+        const int row = t / (kPW / 4), k = t - row * (kPW / 4);
+        const int y = Y0 + row, x = X0 + 4 * k;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (y >= 0 && y < P.ih && x >= 0 && x + 3 < P.ip) v = __ldg(reinterpret_cast<const int4*>(I + (size_t)y * P.ip + x));
+        int* dst = patch + ((row & 1) * 2) * kPlane + (row >> 1) * kQW + 2 * k;
+        *reinterpret_cast<int2*>(dst) = make_int2(v.x, v.z);
+        *reinterpret_cast<int2*>(dst + kPlane) = make_int2(v.y, v.w);
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    float* Rf = Rbase + (size_t)f * P.rstride;
+    const int ix = kTW * tx + lx;
+#pragma unroll
+    for (int hrow = 0; hrow < 2; hrow++) {
+        const int lyy = ly + 8 * hrow;
+        const int iy = kTH * ty + lyy;
+        const int* b = patch + lyy * kQW + lx;
+        layer_smem<3, 0>(P, b, Rf, ix, iy);
+        layer_smem<5, 1>(P, b, Rf, ix, iy);
+        layer_smem<7, 2>(P, b, Rf, ix, iy);
+        layer_smem<9, 3>(P, b, Rf, ix, iy);
+        layer_smem<11, 4>(P, b, Rf, ix, iy);
+    }
+}
+
 cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, float* d_resp, cudaStream_t st) {
-    const dim3 grid(P.hess_tiles, nframes), block(32, 8);
-    hessian_kernel<<<grid, block, 0, st>>>(P, d_integral, d_resp);
+    const OctaveP& q0 = P.oct[0];
+    const bool fast0 = P.sampling == 2 && P.init_lobe == 3 && P.max_scale == 5 && q0.s0 == 0 && q0.nl == 5;
+    int first_tile = 0;
+    if (fast0) {
+        const int tiles_x = (q0.sw + kTW - 1) / kTW, tiles_y = (q0.sh + kTH - 1) / kTH;
+        hessian_o0_kernel<<<dim3(tiles_x * tiles_y, nframes), 256, 0, st>>>(P, d_integral, d_resp, tiles_x);
+        first_tile = P.noctaves > 1 ? P.oct[1].hess_tile0 : P.hess_tiles;
+    }
+    if (P.hess_tiles - first_tile > 0) {
+        const dim3 grid(P.hess_tiles - first_tile, nframes), block(32, 8);
+        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral, d_resp, first_tile);
+    }
     return cudaGetLastError();
 }
 
