@@ -83,7 +83,13 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
                             cudaStream_t st);
 cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, cudaStream_t st);
+// grow-only device scratch of the matcher (split-bf16 operands, per-split group top-2), owned by the context
+struct MatchScratch {
+    void* a = nullptr; void* b = nullptr; void* part = nullptr;
+    size_t cap_a = 0, cap_b = 0, cap_part = 0;
+};
 cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
-                         int nfeatures, cudaStream_t st);
+                         int nfeatures, MatchScratch& ws, int sm_count, cudaStream_t st);
+void free_match_scratch(MatchScratch& ws);
 
 }  // namespace sb

@@ -39,6 +39,7 @@ struct sb_ctx {
     float* d_stage_desc = nullptr;
     int* h_counts = nullptr;          // pinned
     sb_point* h_pts = nullptr;        // pinned, max_pts
+    MatchScratch match_ws;
     std::string err;
 };
 
@@ -158,6 +159,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     cudaFree(ctx->d_integral); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
     cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_stage_img); cudaFree(ctx->d_stage_pts);
     cudaFree(ctx->d_stage_desc);
+    free_match_scratch(ctx->match_ws);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -380,7 +382,9 @@ extern "C" int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1,
     if (n1 == 0) return SB_OK;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    CU(launch_match(d_pts1, n1, d_feat1, d_pts2, n2, d_feat2, ctx->P.nfeatures, st));
+    if (ctx->P.nfeatures != 64 && ctx->P.nfeatures != 128)
+        return fail(ctx, SB_ERR_UNSUPPORTED, "sb_match: the tensor-core matcher is built for 64- and 128-d descriptors (desc_wsz 4)");
+    CU(launch_match(d_pts1, n1, d_feat1, d_pts2, n2, d_feat2, ctx->P.nfeatures, ctx->match_ws, ctx->sm_count, st));
     if (h_pts1) {
         // the five match fields start at SurfPoint::score (surf.cpp:421-425)
         const size_t off = offsetof(sb_point, score);

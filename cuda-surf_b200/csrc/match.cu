@@ -1,99 +1,376 @@
-// match.cu -- brute-force descriptor matching: S = F1 * F2^T, per-row best / second / index, and
-// the five match fields of SurfPoint.
+// match.cu -- brute-force descriptor matching on the 5th-generation tensor cores (tcgen05 + TMEM +
+// TMA), with the reference's top-2 / ambiguity semantics fused into the epilogue.
 //
-// Replaces cuFindMaxCorr / findMaxCorr (surfd.cu:2535-2671, 3550-3566). Reference semantics kept:
-//   * score = dot product accumulated as one FFMA chain over d = 0..nf-1 (surfd.cu:2591-2609);
+// Replaces cuFindMaxCorr / findMaxCorr (surfd.cu:2535-2671, 3550-3566): S = F1 * F2^T, per row of
+// F1 the best and "second" correlation and the five match fields of SurfPoint. It is the only
+// dense contraction of the path. Reference semantics kept (bit-for-bit where they are observable):
+//   * score = dot product accumulated as ONE fp32 FFMA chain over d = 0..nf-1 (surfd.cu:2591-2609);
 //   * candidates are the first n2 - n2%32 descriptors of set 2 (surfd.cu:2569);
-//   * candidates are partitioned into 8 groups g = (p2 % 32) / 4, each keeping a running top-2
-//     with strict > from (0, 0, -1) in increasing p2 (surfd.cu:2610-2625);
-//   * the merge starts from group 0 and sees only the maxima of the other groups
-//     (surfd.cu:2646-2664); ambiguity = second / (best + 1e-6).
+//   * candidates fall into 8 groups g = (p2 % 32) / 4, each keeping a running top-2 with strict >
+//     from (0, 0, -1) in increasing p2 (surfd.cu:2610-2625); the merge starts from group 0 and sees
+//     only the maxima of the other groups (surfd.cu:2646-2664); ambiguity = second / (best + 1e-6).
 // Differences by design: writes are bounded to n1 rows (the reference writes whole 32-row blocks)
-// and match_x/y are left 0 when nothing matched (the reference reads surf2[-1]).
+// and match_x/y stay 0 when nothing matched (the reference reads surf2[-1]).
 //
-// Round-1 kernel: exact fp32 CUDA-core version (row of F1 cached in registers, F2 tiles broadcast
-// from shared memory). The tcgen05 tensor-core version replaces it once detect+describe is pinned.
+// Three launches:
+//   1. match_prep   fp32 descriptors -> bf16 "split" operands A' = [hi | hi | lo], B' = [hi | lo | hi]
+//                   (K = 3*nf), so that A'.B'^T = hi.hi + hi.lo + lo.hi reproduces the fp32 dot product
+//                   to ~2e-5 absolute on unit vectors (plain bf16 would be 4e-3: too coarse to rank).
+//   2. match_mma    one CTA per (128-row block of A', range of column tiles of B'): TMA (128-byte
+//                   swizzle) stages the operand tiles, ONE thread issues tcgen05.mma 128xBNx16 into a
+//                   TMEM accumulator, the four warps read it back with tcgen05.ld and keep, per row and
+//                   group, the running top-2 (value + index) -- the 10 M scores never touch memory.
+//   3. match_final  per row: the 16 group candidates are re-scored with the reference's exact fp32
+//                   FFMA chain, ordered with its update rule, merged with its merge rule and written.
+//                   So score / match are those of the reference unless two candidates of one group
+//                   are closer than the split-bf16 error to the group's second place.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace sb {
 
-template <int NF>
-__global__ void __launch_bounds__(256)
-match_kernel(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, const sb_point* __restrict__ pts2,
-             int n2, const float* __restrict__ f2) {
-    __shared__ __align__(16) float tile2[32][NF];
-    __shared__ float s_max[8][32], s_sec[8][32];
-    __shared__ int s_idx[8][32];
-    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int p1 = blockIdx.x * 32 + lane;
-    const int p1c = min(p1, n1 - 1);
-    float a[NF];
-    {
-        const float4* src = reinterpret_cast<const float4*>(f1 + (size_t)p1c * NF);
-#pragma unroll
-        for (int d = 0; d < NF / 4; d++) {
-            const float4 t = __ldg(src + d);
-            a[4 * d] = t.x; a[4 * d + 1] = t.y; a[4 * d + 2] = t.z; a[4 * d + 3] = t.w;
-        }
+namespace {
+
+constexpr int kBM = 128;        // rows of F1 per CTA == TMEM lanes
+constexpr int kSwizzleRow = 128;  // bytes per operand row chunk (64 bf16) == one 128B-swizzle row
+
+template <int NF> struct MatchCfg {
+    static constexpr int KCH = 3 * NF / 64;            // 64-element K chunks of the split operands
+    static constexpr int KTOT = 3 * NF;                // K of the tensor-core GEMM
+    static constexpr int BN = NF == 64 ? 256 : 128;    // columns (descriptors of set 2) per tile
+    static constexpr int A_BYTES = KCH * kBM * kSwizzleRow;
+    static constexpr int B_BYTES = KCH * BN * kSwizzleRow;
+    static constexpr int SMEM = A_BYTES + B_BYTES + 1024 /*alignment slack*/ + 64 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a mis-programmed pipeline traps (clean launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
     }
-    float mx = 0.f, sc = 0.f;
-    int id = -1;
-    const int ncand = n2 - (n2 & 31);
-    for (int bp2 = 0; bp2 < ncand; bp2 += 32) {
-        __syncthreads();
-        {
-            const float4* src = reinterpret_cast<const float4*>(f2 + (size_t)bp2 * NF);
-            float4* dst = reinterpret_cast<float4*>(&tile2[0][0]);
-            for (int t = threadIdx.x; t < 32 * NF / 4; t += 256) dst[t] = __ldg(src + t);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int dy = 0; dy < 4; dy++) {
-            const float4* b = reinterpret_cast<const float4*>(&tile2[4 * g + dy][0]);
-            float s = 0.f;
-#pragma unroll
-            for (int d = 0; d < NF / 4; d++) {
-                const float4 t = b[d];
-                s = __fmaf_rn(a[4 * d], t.x, s);
-                s = __fmaf_rn(a[4 * d + 1], t.y, s);
-                s = __fmaf_rn(a[4 * d + 2], t.z, s);
-                s = __fmaf_rn(a[4 * d + 3], t.w, s);
-            }
-            if (s > mx) { sc = mx; mx = s; id = bp2 + 4 * g + dy; }
-            else if (s > sc) sc = s;
-        }
-    }
-    s_max[g][lane] = mx; s_sec[g][lane] = sc; s_idx[g][lane] = id;
-    __syncthreads();
-    if (g == 0 && p1 < n1) {
-        float m = s_max[0][lane], s2 = s_sec[0][lane];
-        int idx = s_idx[0][lane];
-#pragma unroll
-        for (int y = 0; y < 8; y++) {
-            const int iy = s_idx[y][lane];
-            const float my = s_max[y][lane];
-            if (idx != iy) {
-                if (my > m) { s2 = fmaxf(m, s2); m = my; idx = iy; }
-                else if (my > s2) s2 = my;
-            }
-        }
-        sb_point* p = pts1 + p1;
-        p->score = m;
-        p->match = idx;
-        p->match_x = idx >= 0 ? pts2[idx].x : 0.f;
-        p->match_y = idx >= 0 ? pts2[idx].y : 0.f;
-        p->ambiguity = __fdiv_rn(s2, __fadd_rn(m, 1e-6f));
-    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// Shared-memory matrix descriptor of a K-major operand tile stored as rows of 128 bytes with the
+// 128-byte swizzle (what TMA writes): start>>4, LBO field 1, SBO = 1024 B between 8-row groups,
+// descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
 }
 
-cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
-                         int nfeatures, cudaStream_t st) {
-    if (n1 <= 0) return cudaSuccess;
-    const dim3 grid((n1 + 31) / 32), block(256);
-    if (nfeatures == 64) match_kernel<64><<<grid, block, 0, st>>>(d_pts1, n1, d_f1, d_pts2, n2, d_f2);
-    else if (nfeatures == 128) match_kernel<128><<<grid, block, 0, st>>>(d_pts1, n1, d_f1, d_pts2, n2, d_f2);
-    else return cudaErrorInvalidValue;
+// ---------------------------------------------------------------------------- 1. operand split
+// rows >= nvalid are zero (padding of A', non-candidates of B'); out: [rows_pad][3*NF] bf16
+template <int NF, bool IS_B>
+__global__ void match_prep(const float* __restrict__ f, int nvalid, int rows_pad, __nv_bfloat16* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = t / NF, d = t - row * NF;
+    if (row >= rows_pad) return;
+    __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+    if (row < nvalid) {
+        const float v = __ldg(f + (size_t)row * NF + d);
+        hi = __float2bfloat16_rn(v);
+        lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    __nv_bfloat16* o = out + (size_t)row * (3 * NF) + d;
+    o[0] = hi;
+    o[NF] = IS_B ? lo : hi;
+    o[2 * NF] = IS_B ? hi : lo;
+}
+
+// ---------------------------------------------------------------------------- 2. tensor-core scores + fused group top-2
+struct Top2 { float mx, sc; int imx, isc; };  // 16 bytes
+
+template <int NF>
+__global__ void __launch_bounds__(128, 1)
+match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles, int tiles_per_split,
+          int n1pad, Top2* __restrict__ part) {
+    using Cfg = MatchCfg<NF>;
+    constexpr int BN = Cfg::BN, KCH = Cfg::KCH;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                    // KCH chunks of 128 rows x 128 B
+    uint8_t* sB = smem + Cfg::A_BYTES;     // KCH chunks of BN rows x 128 B
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + Cfg::B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int rb = blockIdx.x, split = blockIdx.y;
+    const int t0 = split * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
+
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: BN fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    float mx[8], sc[8];
+    int imx[8], isc[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) { mx[g] = 0.f; sc[g] = 0.f; imx[g] = -1; isc[g] = -1; }
+
+    uint32_t ph_load = 0, ph_mma = 0;
+    constexpr uint32_t idesc = umma_idesc(kBM, BN);
+    for (int t = t0; t < t1; t++) {
+        if (tid == 0) {
+            // operands: this tile of B' (and, once, the CTA's rows of A') by TMA into swizzled smem
+            const uint32_t bytes = Cfg::B_BYTES + (t == t0 ? Cfg::A_BYTES : 0);
+            mbar_expect_tx(bar_load, bytes);
+            if (t == t0)
+                for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sA + c * kBM * kSwizzleRow), &mapA, bar_load, c * 64, rb * kBM);
+            for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sB + c * BN * kSwizzleRow), &mapB, bar_load, c * 64, t * BN);
+            mbar_wait(bar_load, ph_load);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // D[128 x BN] = sum over K chunks and 16-element K steps; one thread issues for the CTA
+            for (int c = 0; c < KCH; c++) {
+                const uint64_t da = umma_desc(smem_u32(sA + c * kBM * kSwizzleRow));
+                const uint64_t db = umma_desc(smem_u32(sB + c * BN * kSwizzleRow));
+#pragma unroll
+                for (int k = 0; k < 4; k++)  // +32 bytes (2 x 16 B units) per K step inside the swizzle row
+                    umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
+            }
+            umma_commit(bar_mma);  // arrives when the MMAs above have completed (implies before_thread_sync)
+        }
+        ph_load ^= 1;
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // epilogue: thread == row (TMEM lane); 32 accumulator columns per tcgen05.ld
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + cb, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int col0 = t * BN + cb;  // multiple of 32: group of column j is (j % 32) / 4
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int g = j >> 2;
+                const float s = __uint_as_float(r[j]);
+                if (s > mx[g]) { sc[g] = mx[g]; isc[g] = imx[g]; mx[g] = s; imx[g] = col0 + j; }
+                else if (s > sc[g]) { sc[g] = s; isc[g] = col0 + j; }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // TMEM and the B' buffers are free for the next tile
+    }
+    Top2* dst = part + ((size_t)split * n1pad + (size_t)rb * kBM + tid) * 8;
+#pragma unroll
+    for (int g = 0; g < 8; g++) dst[g] = Top2{mx[g], sc[g], imx[g], isc[g]};
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+}
+
+// ---------------------------------------------------------------------------- 3. exact re-score, group rule, merge
+template <int NF>
+__device__ __forceinline__ float exact_dot(const float* __restrict__ a, const float* __restrict__ b) {
+    float s = 0.f;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll 4
+    for (int d = 0; d < NF / 4; d++) {
+        const float4 x = __ldg(a4 + d), y = __ldg(b4 + d);
+        s = __fmaf_rn(x.x, y.x, s); s = __fmaf_rn(x.y, y.y, s); s = __fmaf_rn(x.z, y.z, s); s = __fmaf_rn(x.w, y.w, s);
+    }
+    return s;
+}
+
+template <int NF>
+__global__ void match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, const sb_point* __restrict__ pts2,
+                            const float* __restrict__ f2, const Top2* __restrict__ part, int nsplit, int n1pad) {
+    const int p1 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p1 >= n1) return;
+    const float* a = f1 + (size_t)p1 * NF;
+    float gmx[8], gsc[8];
+    int gid[8];
+    for (int g = 0; g < 8; g++) {
+        // tensor-core top-2 of the group across the column splits (ties: lower index, as a running scan would)
+        float v1 = 0.f, v2 = 0.f;
+        int i1 = -1, i2 = -1;
+        for (int s = 0; s < nsplit; s++) {
+            const Top2 c = part[((size_t)s * n1pad + p1) * 8 + g];
+            const float cv[2] = {c.mx, c.sc};
+            const int ci[2] = {c.imx, c.isc};
+            for (int k = 0; k < 2; k++) {
+                if (ci[k] < 0) continue;
+                if (cv[k] > v1 || (cv[k] == v1 && i1 >= 0 && ci[k] < i1)) { v2 = v1; i2 = i1; v1 = cv[k]; i1 = ci[k]; }
+                else if (cv[k] > v2 || (cv[k] == v2 && i2 >= 0 && ci[k] < i2)) { v2 = cv[k]; i2 = ci[k]; }
+            }
+        }
+        // the reference's running update (surfd.cu:2610-2625) on the exact fp32 scores, in index order
+        float m = 0.f, s2 = 0.f;
+        int id = -1;
+        int lo = i1, hi = i2;
+        if (lo < 0 || (hi >= 0 && hi < lo)) { const int t = lo; lo = hi; hi = t; }
+        const int order[2] = {lo, hi};
+        for (int k = 0; k < 2; k++) {
+            if (order[k] < 0) continue;
+            const float e = exact_dot<NF>(a, f2 + (size_t)order[k] * NF);
+            if (e > m) { s2 = m; m = e; id = order[k]; }
+            else if (e > s2) s2 = e;
+        }
+        gmx[g] = m; gsc[g] = s2; gid[g] = id;
+    }
+    // merge (surfd.cu:2646-2664): start from group 0, other groups contribute their maxima only
+    float m = gmx[0], s2 = gsc[0];
+    int idx = gid[0];
+    for (int g = 0; g < 8; g++) {
+        if (idx != gid[g]) {
+            if (gmx[g] > m) { s2 = fmaxf(m, s2); m = gmx[g]; idx = gid[g]; }
+            else if (gmx[g] > s2) s2 = gmx[g];
+        }
+    }
+    sb_point* p = pts1 + p1;
+    p->score = m;
+    p->match = idx;
+    p->match_x = idx >= 0 ? pts2[idx].x : 0.f;
+    p->match_y = idx >= 0 ? pts2[idx].y : 0.f;
+    p->ambiguity = __fdiv_rn(s2, __fadd_rn(m, 1e-6f));
+}
+
+// ---------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows][ktot] bf16 row-major; box = 64 elements (128 B) x box_rows, 128-byte swizzle
+bool make_map(CUtensorMap* m, const void* base, int rows, int ktot, int box_rows) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NF>
+cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
+                      MatchScratch& ws, int sm_count, cudaStream_t st) {
+    using Cfg = MatchCfg<NF>;
+    const int ncand = n2 - (n2 & 31);
+    const int n1pad = (n1 + kBM - 1) / kBM * kBM;
+    const int ntiles = (ncand + Cfg::BN - 1) / Cfg::BN;
+    const int n2pad = max(ntiles, 1) * Cfg::BN;
+    const int rbs = n1pad / kBM;
+    int nsplit = ntiles > 0 ? min(ntiles, max(1, (2 * sm_count + rbs - 1) / rbs)) : 1;
+    const int tiles_per_split = ntiles > 0 ? (ntiles + nsplit - 1) / nsplit : 0;
+    if (ntiles > 0) nsplit = (ntiles + tiles_per_split - 1) / tiles_per_split;
+    // scratch (grow-only)
+    const size_t needA = (size_t)n1pad * Cfg::KTOT * 2, needB = (size_t)n2pad * Cfg::KTOT * 2;
+    const size_t needP = (size_t)nsplit * n1pad * 8 * sizeof(Top2);
+    cudaError_t e;
+    auto grow = [&](void*& p, size_t& cap, size_t need) -> cudaError_t {
+        if (cap >= need) return cudaSuccess;
+        if (p) { cudaError_t r = cudaFree(p); if (r != cudaSuccess) return r; p = nullptr; cap = 0; }
+        cudaError_t r = cudaMalloc(&p, need);
+        if (r == cudaSuccess) cap = need;
+        return r;
+    };
+    if ((e = grow(ws.a, ws.cap_a, needA)) != cudaSuccess) return e;
+    if ((e = grow(ws.b, ws.cap_b, needB)) != cudaSuccess) return e;
+    if ((e = grow(ws.part, ws.cap_part, needP)) != cudaSuccess) return e;
+
+    match_prep<NF, false><<<(n1pad * NF + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a);
+    match_prep<NF, true><<<(n2pad * NF + 255) / 256, 256, 0, st>>>(d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b);
+    CUtensorMap mapA, mapB;
+    if (!make_map(&mapA, ws.a, n1pad, Cfg::KTOT, kBM) || !make_map(&mapB, ws.b, n2pad, Cfg::KTOT, Cfg::BN)) return cudaErrorNotSupported;
+    if ((e = cudaFuncSetAttribute(match_mma<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
+    match_mma<NF><<<dim3(rbs, nsplit), 128, Cfg::SMEM, st>>>(mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
+    match_final<NF><<<(n1 + 127) / 128, 128, 0, st>>>(d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit, n1pad);
     return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
+                         int nfeatures, MatchScratch& ws, int sm_count, cudaStream_t st) {
+    if (n1 <= 0) return cudaSuccess;
+    if (nfeatures == 64) return run_match<64>(d_pts1, n1, d_f1, d_pts2, n2, d_f2, ws, sm_count, st);
+    if (nfeatures == 128) return run_match<128>(d_pts1, n1, d_f1, d_pts2, n2, d_f2, ws, sm_count, st);
+    return cudaErrorInvalidValue;  // desc_wsz < 4: no tensor-core tiling for K < 64 yet
+}
+
+void free_match_scratch(MatchScratch& ws) {
+    cudaFree(ws.a); cudaFree(ws.b); cudaFree(ws.part);
+    ws = MatchScratch{};
 }
 
 }  // namespace sb
