@@ -116,29 +116,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------------------- 1. operand split
-// rows >= nvalid are zero (padding of A', non-candidates of B'); out: [rows_pad][3*NF] bf16
-template <int NF, bool IS_B>
-__global__ void match_prep(const float* __restrict__ f, int nvalid, int rows_pad, __nv_bfloat16* __restrict__ out) {
+// rows >= nvalid are zero (padding of A', non-candidates of B'); out: [rows_pad][3*NF] bf16. One launch for both sets.
+template <int NF>
+__global__ void match_prep(const float* __restrict__ fa, int na, int na_pad, __nv_bfloat16* __restrict__ outa,
+                           const float* __restrict__ fb, int nb, int nb_pad, __nv_bfloat16* __restrict__ outb) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = t / NF, d = t - row * NF;
-    if (row >= rows_pad) return;
+    int row = t / NF;
+    const int d = t - row * NF;
+    const bool is_b = row >= na_pad;
+    if (is_b) row -= na_pad;
+    if (is_b && row >= nb_pad) return;
+    const float* f = is_b ? fb : fa;
+    const int nvalid = is_b ? nb : na;
     __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
     if (row < nvalid) {
         const float v = __ldg(f + (size_t)row * NF + d);
         hi = __float2bfloat16_rn(v);
         lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     }
-    __nv_bfloat16* o = out + (size_t)row * (3 * NF) + d;
+    __nv_bfloat16* o = (is_b ? outb : outa) + (size_t)row * (3 * NF) + d;
     o[0] = hi;
-    o[NF] = IS_B ? lo : hi;
-    o[2 * NF] = IS_B ? hi : lo;
+    o[NF] = is_b ? lo : hi;
+    o[2 * NF] = is_b ? hi : lo;
 }
 
 // ---------------------------------------------------------------------------- 2. tensor-core scores + fused group top-2
 struct Top2 { float mx, sc; int imx, isc; };  // 16 bytes
 
 template <int NF>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles, int tiles_per_split,
           int n1pad, Top2* __restrict__ part) {
     using Cfg = MatchCfg<NF>;
@@ -151,6 +157,8 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int quarter = warp & 3;    // TMEM lane quarter this warp may read (warp id % 4)
+    const int chalf = warp >> 2;     // which half of the tile's columns this warp scans
     const int rb = blockIdx.x, split = blockIdx.y;
     const int t0 = split * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
 
@@ -200,25 +208,30 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // epilogue: thread == row (TMEM lane); 32 accumulator columns per tcgen05.ld
+        // epilogue: thread == (row = TMEM lane, half of the columns); 32 accumulator columns per tcgen05.ld.
+        // Branch-free running top-2 per group: values with max/min, indices with selects; the 8 groups
+        // of a 32-column chunk are independent dependency chains (ILP 8).
 #pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 32) {
+        for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
             uint32_t r[32];
-            tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + cb, r);
+            tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + cb, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             const int col0 = t * BN + cb;  // multiple of 32: group of column j is (j % 32) / 4
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const int g = j >> 2;
                 const float s = __uint_as_float(r[j]);
-                if (s > mx[g]) { sc[g] = mx[g]; isc[g] = imx[g]; mx[g] = s; imx[g] = col0 + j; }
-                else if (s > sc[g]) { sc[g] = s; isc[g] = col0 + j; }
+                const bool gt1 = s > mx[g], gt2 = s > sc[g];
+                isc[g] = gt1 ? imx[g] : (gt2 ? col0 + j : isc[g]);
+                imx[g] = gt1 ? col0 + j : imx[g];
+                sc[g] = fmaxf(sc[g], fminf(mx[g], s));
+                mx[g] = fmaxf(mx[g], s);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // TMEM and the B' buffers are free for the next tile
     }
-    Top2* dst = part + ((size_t)split * n1pad + (size_t)rb * kBM + tid) * 8;
+    Top2* dst = part + ((size_t)(split * 2 + chalf) * n1pad + (size_t)rb * kBM + quarter * 32 + (tid & 31)) * 8;
 #pragma unroll
     for (int g = 0; g < 8; g++) dst[g] = Top2{mx[g], sc[g], imx[g], isc[g]};
     __syncthreads();
@@ -239,57 +252,68 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ a, const fl
     return s;
 }
 
+// One WARP per row of set 1. Lane (2g + k), k in {0,1}, owns candidate k of group g: it picks the
+// k-th best tensor-core score of the group across the column splits, re-scores it with the
+// reference's exact fp32 FFMA chain (a chain cannot be split across lanes), and the pair is
+// combined with the reference's running update in index order; lane 0 then applies the merge.
 template <int NF>
-__global__ void match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, const sb_point* __restrict__ pts2,
-                            const float* __restrict__ f2, const Top2* __restrict__ part, int nsplit, int n1pad) {
-    const int p1 = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128)
+match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, const sb_point* __restrict__ pts2,
+            const float* __restrict__ f2, const Top2* __restrict__ part, int nsplit, int n1pad) {
+    const int lane = threadIdx.x & 31;
+    const int p1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p1 >= n1) return;
-    const float* a = f1 + (size_t)p1 * NF;
-    float gmx[8], gsc[8];
-    int gid[8];
-    for (int g = 0; g < 8; g++) {
-        // tensor-core top-2 of the group across the column splits (ties: lower index, as a running scan would)
-        float v1 = 0.f, v2 = 0.f;
-        int i1 = -1, i2 = -1;
-        for (int s = 0; s < nsplit; s++) {
-            const Top2 c = part[((size_t)s * n1pad + p1) * 8 + g];
-            const float cv[2] = {c.mx, c.sc};
-            const int ci[2] = {c.imx, c.isc};
-            for (int k = 0; k < 2; k++) {
-                if (ci[k] < 0) continue;
-                if (cv[k] > v1 || (cv[k] == v1 && i1 >= 0 && ci[k] < i1)) { v2 = v1; i2 = i1; v1 = cv[k]; i1 = ci[k]; }
-                else if (cv[k] > v2 || (cv[k] == v2 && i2 >= 0 && ci[k] < i2)) { v2 = cv[k]; i2 = ci[k]; }
-            }
-        }
-        // the reference's running update (surfd.cu:2610-2625) on the exact fp32 scores, in index order
-        float m = 0.f, s2 = 0.f;
-        int id = -1;
-        int lo = i1, hi = i2;
-        if (lo < 0 || (hi >= 0 && hi < lo)) { const int t = lo; lo = hi; hi = t; }
-        const int order[2] = {lo, hi};
-        for (int k = 0; k < 2; k++) {
-            if (order[k] < 0) continue;
-            const float e = exact_dot<NF>(a, f2 + (size_t)order[k] * NF);
-            if (e > m) { s2 = m; m = e; id = order[k]; }
-            else if (e > s2) s2 = e;
-        }
-        gmx[g] = m; gsc[g] = s2; gid[g] = id;
-    }
-    // merge (surfd.cu:2646-2664): start from group 0, other groups contribute their maxima only
-    float m = gmx[0], s2 = gsc[0];
-    int idx = gid[0];
-    for (int g = 0; g < 8; g++) {
-        if (idx != gid[g]) {
-            if (gmx[g] > m) { s2 = fmaxf(m, s2); m = gmx[g]; idx = gid[g]; }
-            else if (gmx[g] > s2) s2 = gmx[g];
+    const int g = (lane >> 1) & 7, k = lane & 1;
+    // tensor-core top-2 of the group across the splits (ties: lower index, as a running scan would keep)
+    float v1 = 0.f, v2 = 0.f;
+    int i1 = -1, i2 = -1;
+    for (int s = 0; s < nsplit; s++) {
+        const Top2 c = part[((size_t)s * n1pad + p1) * 8 + g];  // 128 contiguous bytes per (split,row) across the warp
+        const float cv[2] = {c.mx, c.sc};
+        const int ci[2] = {c.imx, c.isc};
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (ci[q] < 0) continue;
+            if (cv[q] > v1 || (cv[q] == v1 && i1 >= 0 && ci[q] < i1)) { v2 = v1; i2 = i1; v1 = cv[q]; i1 = ci[q]; }
+            else if (cv[q] > v2 || (cv[q] == v2 && i2 >= 0 && ci[q] < i2)) { v2 = cv[q]; i2 = ci[q]; }
         }
     }
-    sb_point* p = pts1 + p1;
-    p->score = m;
-    p->match = idx;
-    p->match_x = idx >= 0 ? pts2[idx].x : 0.f;
-    p->match_y = idx >= 0 ? pts2[idx].y : 0.f;
-    p->ambiguity = __fdiv_rn(s2, __fadd_rn(m, 1e-6f));
+    // candidate of this lane: the pair in increasing index order (k = 0 first)
+    int lo = i1, hi = i2;
+    if (lo < 0 || (hi >= 0 && hi < lo)) { const int t = lo; lo = hi; hi = t; }
+    const int mine = k == 0 ? lo : hi;
+    float e = 0.f;
+    if (lane < 16 && mine >= 0) e = exact_dot<NF>(f1 + (size_t)p1 * NF, f2 + (size_t)mine * NF);
+    // the reference's running update (surfd.cu:2610-2625) over (first, second) in index order
+    const float e0 = __shfl_sync(0xffffffffu, e, lane & ~1), e1 = __shfl_sync(0xffffffffu, e, lane | 1);
+    const int c0 = __shfl_sync(0xffffffffu, mine, lane & ~1), c1 = __shfl_sync(0xffffffffu, mine, lane | 1);
+    float gm = 0.f, gs = 0.f;
+    int gi = -1;
+    if (c0 >= 0 && e0 > gm) { gm = e0; gi = c0; }
+    if (c1 >= 0) {
+        if (e1 > gm) { gs = gm; gm = e1; gi = c1; }
+        else if (e1 > gs) gs = e1;
+    }
+    // merge (surfd.cu:2646-2664): start from group 0, the other groups contribute their maxima only
+    float m = __shfl_sync(0xffffffffu, gm, 0), s2 = __shfl_sync(0xffffffffu, gs, 0);
+    int idx = __shfl_sync(0xffffffffu, gi, 0);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float qm = __shfl_sync(0xffffffffu, gm, 2 * q);
+        const int qi = __shfl_sync(0xffffffffu, gi, 2 * q);
+        if (idx != qi) {
+            if (qm > m) { s2 = fmaxf(m, s2); m = qm; idx = qi; }
+            else if (qm > s2) s2 = qm;
+        }
+    }
+    if (lane == 0) {
+        sb_point* p = pts1 + p1;
+        p->score = m;
+        p->match = idx;
+        p->match_x = idx >= 0 ? pts2[idx].x : 0.f;
+        p->match_y = idx >= 0 ? pts2[idx].y : 0.f;
+        p->ambiguity = __fdiv_rn(s2, __fadd_rn(m, 1e-6f));
+    }
 }
 
 // ---------------------------------------------------------------------------- host
@@ -330,12 +354,13 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     const int ntiles = (ncand + Cfg::BN - 1) / Cfg::BN;
     const int n2pad = max(ntiles, 1) * Cfg::BN;
     const int rbs = n1pad / kBM;
-    int nsplit = ntiles > 0 ? min(ntiles, max(1, (2 * sm_count + rbs - 1) / rbs)) : 1;
+    // about one CTA per SM (one wave): a CTA's fixed cost (TMEM allocation, its A' rows) is amortised over its tiles
+    int nsplit = ntiles > 0 ? min(ntiles, max(1, sm_count / rbs)) : 1;
     const int tiles_per_split = ntiles > 0 ? (ntiles + nsplit - 1) / nsplit : 0;
     if (ntiles > 0) nsplit = (ntiles + tiles_per_split - 1) / tiles_per_split;
     // scratch (grow-only)
     const size_t needA = (size_t)n1pad * Cfg::KTOT * 2, needB = (size_t)n2pad * Cfg::KTOT * 2;
-    const size_t needP = (size_t)nsplit * n1pad * 8 * sizeof(Top2);
+    const size_t needP = (size_t)nsplit * 2 * n1pad * 8 * sizeof(Top2);  // two column halves per split
     cudaError_t e;
     auto grow = [&](void*& p, size_t& cap, size_t need) -> cudaError_t {
         if (cap >= need) return cudaSuccess;
@@ -348,13 +373,16 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     if ((e = grow(ws.b, ws.cap_b, needB)) != cudaSuccess) return e;
     if ((e = grow(ws.part, ws.cap_part, needP)) != cudaSuccess) return e;
 
-    match_prep<NF, false><<<(n1pad * NF + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a);
-    match_prep<NF, true><<<(n2pad * NF + 255) / 256, 256, 0, st>>>(d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b);
+    match_prep<NF><<<((n1pad + n2pad) * NF + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a, d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b);
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, ws.a, n1pad, Cfg::KTOT, kBM) || !make_map(&mapB, ws.b, n2pad, Cfg::KTOT, Cfg::BN)) return cudaErrorNotSupported;
-    if ((e = cudaFuncSetAttribute(match_mma<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
-    match_mma<NF><<<dim3(rbs, nsplit), 128, Cfg::SMEM, st>>>(mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
-    match_final<NF><<<(n1 + 127) / 128, 128, 0, st>>>(d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit, n1pad);
+    static bool attr_set = false;  // per template instance; the attribute is per function, not per context
+    if (!attr_set) {
+        if ((e = cudaFuncSetAttribute(match_mma<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
+        attr_set = true;
+    }
+    match_mma<NF><<<dim3(rbs, nsplit), 256, Cfg::SMEM, st>>>(mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
+    match_final<NF><<<(n1 + 3) / 4, 128, 0, st>>>(d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit * 2, n1pad);
     return cudaGetLastError();
 }
 

@@ -116,6 +116,14 @@ class Surfor:
                               data2.d_data.data_ptr(), data2.num_pts, features2.data_ptr())
         B.check(rc, self._ctx)
 
+    def match_async(self, data1, data2, features1, features2, stream=None):
+        """match() enqueued on a torch stream (default: current), device results only, no synchronisation"""
+        import torch
+        st = (stream or torch.cuda.current_stream(features1.device)).cuda_stream
+        rc = B.lib().sb_match_async(self._ctx, data1.d_data.data_ptr(), data1.num_pts, features1.data_ptr(),
+                                    data2.d_data.data_ptr(), data2.num_pts, features2.data_ptr(), C.c_void_p(st))
+        B.check(rc, self._ctx)
+
     # ---- batched forms (frame loop of main.cpp:239-245 without per-frame host round trips) ----------
     def detect_batch(self, images, pitch, points, counts, desc=None, stream=None):
         """images uint8 CUDA [n, h, pitch]; points uint8 CUDA [n, max_pts*48]; counts int32 CUDA [n];

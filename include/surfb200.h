@@ -100,6 +100,11 @@ int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w, int h, int
 int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const float* d_feat1, const sb_point* d_pts2,
              int n2, const float* d_feat2);
 
+/* The same matching, enqueued on `stream` (used as given) with no host copy and no synchronisation:
+ * for pipelines that keep stereo pairs on the device (BASELINE config 5).                       */
+int sb_match_async(sb_ctx* ctx, sb_point* d_pts1, int n1, const float* d_feat1, const sb_point* d_pts2, int n2,
+                   const float* d_feat2, void* stream);
+
 /* Batched, asynchronous form of detectAndCompute for independent frames (the frame loop of
  * main.cpp:239-245 without a host round trip per frame). nframes <= params.batch.
  *   d_images  frame f at d_images + f*image_stride (bytes), row pitch `pitch`

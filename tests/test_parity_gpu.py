@@ -258,6 +258,39 @@ def test_match_vs_oracle_and_tail_rule():
         assert np.allclose(got["ambiguity"], want["ambiguity"], atol=1e-6)
 
 
+@pytest.mark.parametrize("nf,n1,n2", [(64, 2739, 3443), (128, 700, 1500), (64, 128, 256), (128, 1, 40)])
+def test_match_large_and_surf128_vs_oracle(nf, n1, n2):
+    """several row blocks, column tiles and splits of the tensor-core matcher; 128-d uses the 128-column tile"""
+    sb = _sb()
+    torch = _torch()
+    rng = np.random.default_rng(nf + n1)
+    # correlated descriptors (a few shared directions + noise) so that best / second are close, as on real data
+    basis = rng.standard_normal((24, nf)).astype(np.float32)
+    f1 = (rng.random((n1, 24)).astype(np.float32) @ basis + 0.3 * rng.standard_normal((n1, nf)).astype(np.float32))
+    f2 = (rng.random((n2, 24)).astype(np.float32) @ basis + 0.3 * rng.standard_normal((n2, nf)).astype(np.float32))
+    f1 = np.abs(f1) / np.linalg.norm(f1, axis=1, keepdims=True)
+    f2 = np.abs(f2) / np.linalg.norm(f2, axis=1, keepdims=True)
+    p1 = np.zeros(n1, ol.POINT_DTYPE)
+    p2 = np.zeros(n2, ol.POINT_DTYPE)
+    p2["x"] = rng.random(n2).astype(np.float32) * 100
+    p2["y"] = rng.random(n2).astype(np.float32) * 100
+    want = ol.match(p1, f1, p2, f2)
+    det = make_det(64, 64, 1, extend=(nf == 128), max_pts=4096)
+    a = sb.initSurfData(4096)
+    b = sb.initSurfData(4096)
+    a.num_pts, b.num_pts = n1, n2
+    a.d_data[: n1 * 48] = torch.from_numpy(p1.view(np.uint8)).cuda()
+    b.d_data[: n2 * 48] = torch.from_numpy(p2.view(np.uint8)).cuda()
+    det.match(a, b, torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda())
+    got = a.host_points()
+    same = got["match"] == want["match"]
+    assert same.mean() >= 0.999, f"match index differs for {(~same).sum()} of {n1} rows"
+    assert np.array_equal(got["score"][same], want["score"][same])
+    assert np.array_equal(got["match_x"][same], want["match_x"][same])
+    close = np.abs(got["ambiguity"] - want["ambiguity"]) <= 1e-4
+    assert close.mean() >= 0.999, f"ambiguity differs for {(~close).sum()} rows, max {np.abs(got['ambiguity'] - want['ambiguity']).max()}"
+
+
 def test_golden_pair_counts():
     """committed golden vectors of the reference (skips until they exist)"""
     g = load_golden("pair_left_upright")
