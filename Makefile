@@ -22,9 +22,13 @@ build/synth.o: $(CSRC)/synth.cpp include/surfb200.h
 $(LIB): $(OBJS)
 	$(NVCC) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
 
+# the reference's main.cpp flow on this library (include/compat/surf.h), no OpenCV
+demo: $(LIB) examples/surf_demo.cpp include/compat/surf.h
+	$(NVCC) -O2 -std=c++17 -Iinclude -Iinclude/compat -o build/surf_demo examples/surf_demo.cpp -L$(PKG) -lsurfb200 -Xlinker -rpath -Xlinker '$$ORIGIN/../$(PKG)'
+
 oracle:
 	env -u CC $(MAKE) -C oracle all
 
 clean:
 	rm -rf build $(LIB)
-.PHONY: all oracle clean
+.PHONY: all oracle clean demo
