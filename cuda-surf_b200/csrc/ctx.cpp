@@ -11,6 +11,7 @@
 // surf.cpp:345-349 are gone), and a frame is 5 kernel launches with no host round trip.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +29,9 @@ struct sb_ctx {
     PipeP P{};
     int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
+    // ingest / egress streams and per-chunk events of the pipelined host-buffer path (sb_detect_batch_host)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
     // scratch, `batch` frame slots each
     int* d_integral = nullptr;
     float* d_resp = nullptr;
@@ -165,6 +169,10 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
     if (ctx->h_match) cudaFreeHost(ctx->h_match);
+    for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -242,20 +250,27 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
 
 // Enqueue integral -> Hessian -> NMS(+refine, append) -> clamp [-> orientation] -> descriptors.
 // ev: optional 5 events recorded at the stage boundaries (profiling entry point only).
+// The frames use scratch slots [slot0, slot0 + nframes).
 static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
-                          sb_point* d_points, int* d_counts, float* d_desc, cudaStream_t st, cudaEvent_t* ev = nullptr) {
+                          sb_point* d_points, int* d_counts, float* d_desc, cudaStream_t st, cudaEvent_t* ev = nullptr,
+                          int slot0 = 0) {
     const PipeP& P = ctx->P;
+    int* integral = ctx->d_integral + (size_t)slot0 * P.istride;
+    float* resp = ctx->d_resp + (size_t)slot0 * P.rstride;
+    int* colsum = ctx->d_colsum + (size_t)slot0 * P.nbands * P.nchunks * 256;
+    int* rowsum = ctx->d_rowsum + (size_t)slot0 * P.nbands * 32 * P.nchunks;
+    int* tilesum = ctx->d_tilesum + (size_t)slot0 * P.nbands * P.nchunks;
     CU(cudaMemsetAsync(d_counts, 0, sizeof(int) * nframes, st));
     if (ev) CU(cudaEventRecord(ev[0], st));
-    CU(launch_integral(P, d_images, image_stride, pitch, nframes, ctx->d_integral, ctx->d_colsum, ctx->d_rowsum, ctx->d_tilesum, st));
+    CU(launch_integral(P, d_images, image_stride, pitch, nframes, integral, colsum, rowsum, tilesum, st));
     if (ev) CU(cudaEventRecord(ev[1], st));
-    CU(launch_hessian(P, nframes, ctx->d_integral, ctx->d_resp, st));
+    CU(launch_hessian(P, nframes, integral, resp, st));
     if (ev) CU(cudaEventRecord(ev[2], st));
-    CU(launch_nms(P, nframes, ctx->d_integral, ctx->d_resp, d_points, d_counts, st));
+    CU(launch_nms(P, nframes, integral, resp, d_points, d_counts, st));
     CU(launch_clamp_counts(d_counts, nframes, P.max_pts, st));
     if (ev) CU(cudaEventRecord(ev[3], st));
     if (d_desc)
-        CU(launch_describe(P, nframes, ctx->d_integral, d_points, P.max_pts, d_counts, -1, d_desc,
+        CU(launch_describe(P, nframes, integral, d_points, P.max_pts, d_counts, -1, d_desc,
                            (long long)P.max_pts * P.nfeatures, ctx->sm_count, st));
     if (ev) CU(cudaEventRecord(ev[4], st));
     return SB_OK;
@@ -350,29 +365,60 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
         CU(cudaMalloc((void**)&ctx->d_stage_pts, sizeof(sb_point) * (size_t)P.max_pts * B));
         CU(cudaMalloc((void**)&ctx->d_stage_desc, sizeof(float) * (size_t)P.max_pts * P.nfeatures * B));
     }
+    // Pipelined ingest / compute / egress. The batch is cut into chunks; chunk k's frames go up on the
+    // ingest stream, its kernels run on the compute stream behind an event, and as soon as its keypoint
+    // counts are visible on the host the exact-size copies of its points and descriptors are queued on
+    // the egress stream -- so the H2D of chunk k+1, the kernels of chunk k and the D2H of chunk k-1
+    // overlap (two copy engines, PCIe is full duplex). The reference does all of this serially per frame
+    // with blocking copies (main.cpp:211-226, surf.cpp:302-303, 335-342).
+    const int chunk = nframes >= 32 ? 8 : (nframes >= 8 ? 4 : 1);
+    const int nchunks = (nframes + chunk - 1) / chunk;
+    if (!ctx->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    }
+    while ((int)ctx->ev_in.size() < nchunks) {
+        cudaEvent_t a = nullptr, b = nullptr;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        ctx->ev_in.push_back(a);
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ctx->ev_done.push_back(b);
+    }
     cudaStream_t st = ctx->stream;
-    if (dpitch == P.w) {
-        CU(cudaMemcpyAsync(ctx->d_stage_img, h_images, fbytes * nframes, cudaMemcpyHostToDevice, st));
-    } else {
-        for (int f = 0; f < nframes; f++)
-            CU(cudaMemcpy2DAsync(ctx->d_stage_img + f * dstride, dpitch, h_images + f * fbytes, P.w, P.w, P.h,
-                                 cudaMemcpyHostToDevice, st));
+    const size_t pstride = (size_t)P.max_pts, dstride_f = (size_t)P.max_pts * P.nfeatures;
+    for (int k = 0; k < nchunks; k++) {
+        const int f0 = k * chunk, nf = std::min(chunk, nframes - f0);
+        if (dpitch == P.w) {
+            CU(cudaMemcpyAsync(ctx->d_stage_img + f0 * dstride, h_images + f0 * fbytes, fbytes * nf, cudaMemcpyHostToDevice, ctx->s_h2d));
+        } else {
+            for (int f = f0; f < f0 + nf; f++)
+                CU(cudaMemcpy2DAsync(ctx->d_stage_img + f * dstride, dpitch, h_images + f * fbytes, P.w, P.w, P.h,
+                                     cudaMemcpyHostToDevice, ctx->s_h2d));
+        }
+        CU(cudaEventRecord(ctx->ev_in[k], ctx->s_h2d));
+        CU(cudaStreamWaitEvent(st, ctx->ev_in[k], 0));
+        const int rc = enqueue_frames(ctx, ctx->d_stage_img + f0 * dstride, dstride, dpitch, nf, ctx->d_stage_pts + f0 * pstride,
+                                      ctx->d_counts + f0, h_desc ? ctx->d_stage_desc + f0 * dstride_f : nullptr, st, nullptr, f0);
+        if (rc != SB_OK) return rc;
+        // counts land in the context's pinned array (the caller's may be pageable, which would block here)
+        CU(cudaMemcpyAsync(ctx->h_counts + f0, ctx->d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx->ev_done[k], st));
     }
-    const int rc = enqueue_frames(ctx, ctx->d_stage_img, dstride, dpitch, nframes, ctx->d_stage_pts, ctx->d_counts,
-                                  h_desc ? ctx->d_stage_desc : nullptr, st);
-    if (rc != SB_OK) return rc;
-    CU(cudaMemcpyAsync(h_counts, ctx->d_counts, sizeof(int) * nframes, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    // second leg: only the keypoints that exist
-    for (int f = 0; f < nframes; f++) {
-        const int n = h_counts[f];
-        if (n <= 0) continue;
-        CU(cudaMemcpyAsync(h_points + (size_t)f * P.max_pts, ctx->d_stage_pts + (size_t)f * P.max_pts, sizeof(sb_point) * n,
-                           cudaMemcpyDeviceToHost, st));
-        if (h_desc)
-            CU(cudaMemcpyAsync(h_desc + (size_t)f * P.max_pts * P.nfeatures, ctx->d_stage_desc + (size_t)f * P.max_pts * P.nfeatures,
-                               sizeof(float) * (size_t)n * P.nfeatures, cudaMemcpyDeviceToHost, st));
+    for (int k = 0; k < nchunks; k++) {
+        const int f0 = k * chunk, nf = std::min(chunk, nframes - f0);
+        CU(cudaEventSynchronize(ctx->ev_done[k]));  // counts of chunk k are on the host; later chunks keep running
+        CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[k], 0));
+        for (int f = f0; f < f0 + nf; f++) {
+            const int n = h_counts[f] = ctx->h_counts[f];
+            if (n <= 0) continue;  // only the keypoints that exist travel
+            CU(cudaMemcpyAsync(h_points + f * pstride, ctx->d_stage_pts + f * pstride, sizeof(sb_point) * n,
+                               cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (h_desc)
+                CU(cudaMemcpyAsync(h_desc + f * dstride_f, ctx->d_stage_desc + f * dstride_f,
+                                   sizeof(float) * (size_t)n * P.nfeatures, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
     }
+    CU(cudaStreamSynchronize(ctx->s_d2h));
     CU(cudaStreamSynchronize(st));
     return SB_OK;
 }

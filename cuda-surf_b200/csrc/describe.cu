@@ -452,25 +452,40 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                     }
                     emit_row<O>(h, lane, W, k, ci, cfrac1, cfrac, v);
                 };
-                // The 12 gathers of a sample: rows r-S (m), r (z), r+1 (u), r+S+1 (q); columns c-S (A), c (B),
-                // c+1 (C), c+S+1 (D). Software-pipelined: the gathers of this lane's NEXT row are issued before
-                // the current row is consumed, so a warp always has 12 loads in flight (the loop is latency-bound).
-                auto gather = [&](int rowoff, int (&g)[12]) {
-                    const int om = rowoff - sip, o1 = rowoff + ip, op = rowoff + sip1;
-                    g[0] = __ldg(pA + om); g[1] = __ldg(pB + om); g[2] = __ldg(pB + om + 1); g[3] = __ldg(pD + om);
-                    g[4] = __ldg(pA + rowoff); g[5] = __ldg(pD + rowoff);
-                    g[6] = __ldg(pA + o1); g[7] = __ldg(pD + o1);
-                    g[8] = __ldg(pA + op); g[9] = __ldg(pB + op); g[10] = __ldg(pB + op + 1); g[11] = __ldg(pD + op);
+                // The 12 corner values of a sample: rows r-S (m), r (z), r+1 (u), r+S+1 (q); columns c-S (A), c (B),
+                // c+1 (C), c+S+1 (D); m and q need all four columns, z and u only A and D.
+                // Because step = rn(sc/2) and S = rz(sc), S = 2*step - e with e in {0,1}, and this lane visits
+                // lattice rows i, i+2, ... (pixel rows 2*step apart). Hence the row r-S of this iteration is the
+                // row X = r+e of the previous one, and the row Y = r+1-e of this iteration is the previous row
+                // r+S+1: 6 of the 12 values are carried in registers and an iteration gathers 8 (rows X and q),
+                //   haar_x = (qD + mB - mD - qB) - (qC + mA - mC - qA)
+                //   haar_y = (XD - XA) + (YD - YA) - (mD - mA) - (qD - qA)      (symmetric in z/u, so X/Y need no
+                // case split). Software-pipelined: the gathers of this lane's NEXT row are issued before the
+                // current row is consumed.
+                const int e = 2 * step - S;
+                const bool carry = (e == 0 || e == 1);
+                const int offX = carry ? e * ip : 0, offY = carry ? ip - offX : ip;
+                auto gather8 = [&](int rowoff, int (&g)[8]) {
+                    const int ox = rowoff + offX, op = rowoff + sip1;
+                    g[0] = __ldg(pA + ox); g[1] = __ldg(pB + ox); g[2] = __ldg(pB + ox + 1); g[3] = __ldg(pD + ox);
+                    g[4] = __ldg(pA + op); g[5] = __ldg(pB + op); g[6] = __ldg(pB + op + 1); g[7] = __ldg(pD + op);
                 };
                 int ii = row_lo + half;
                 RowEntry t;
-                int g[12];
-                if (ii < row_hi) { t = rowT[ii]; gather(t.rowoff, g); }
+                int g[8];
+                int m0 = 0, m1 = 0, m2 = 0, m3 = 0, yA = 0, yD = 0;
+                if (ii < row_hi) {
+                    t = rowT[ii];
+                    gather8(t.rowoff, g);
+                    const int om = t.rowoff - sip, oy = t.rowoff + offY;
+                    m0 = __ldg(pA + om); m1 = __ldg(pB + om); m2 = __ldg(pB + om + 1); m3 = __ldg(pD + om);
+                    yA = __ldg(pA + oy); yD = __ldg(pD + oy);
+                }
                 while (ii < row_hi) {
                     const int in = ii + 2;
                     RowEntry tn = t;
-                    int gn[12];
-                    if (in < row_hi) { tn = rowT[in]; gather(tn.rowoff, gn); }
+                    int gn[8];
+                    if (in < row_hi) { tn = rowT[in]; gather8(tn.rowoff, gn); }
                     if (t.ri != cur) {
                         if (cur != kRowInvalid) {
                             flush(cur, sl, xl);
@@ -485,10 +500,15 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                         }
                         cur = t.ri;
                     }
+                    if (!carry) {
+                        // generic (S, step): rows z = r and u = r+1 are gathered as X and Y, m is re-read
+                        const int om = t.rowoff - sip, oy = t.rowoff + offY;
+                        m0 = __ldg(pA + om); m1 = __ldg(pB + om); m2 = __ldg(pB + om + 1); m3 = __ldg(pD + om);
+                        yA = __ldg(pA + oy); yD = __ldg(pD + oy);
+                    }
                     const float weight = s_lut2[__float2int_rz(__fmaf_rn(t.rpos, t.rpos, cpos2))];
-                    // haar_x = box(c..c+S, r-S..r+S) - box(c-S..c, r-S..r+S); haar_y = box(c-S..c+S, r-S..r) - box(.., r..r+S)
-                    const int wx = (g[11] + g[1] - g[3] - g[9]) - (g[10] + g[0] - g[2] - g[8]);
-                    const int wy = (g[7] + g[0] - g[3] - g[6]) - (g[11] + g[4] - g[5] - g[8]);
+                    const int wx = (g[7] + m1 - m3 - g[5]) - (g[6] + m0 - m2 - g[4]);
+                    const int wy = (g[3] - g[0]) + (yD - yA) - (m3 - m0) - (g[7] - g[4]);
                     const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(wx)), kR255);
                     const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(wy)), kR255);
                     const float w1 = t.rfrac, w0 = __fsub_rn(1.f, w1);
@@ -504,9 +524,11 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                         xh[0] = __fmaf_rn(an, w1, xh[0]); xh[1] = __fmaf_rn(fabsf(an), w1, xh[1]);
                         xh[2] = __fmaf_rn(bn, w1, xh[2]); xh[3] = __fmaf_rn(fabsf(bn), w1, xh[3]);
                     }
+                    // carry: this row's X becomes the next row's m, this row's q(A,D) its Y
+                    m0 = g[0]; m1 = g[1]; m2 = g[2]; m3 = g[3]; yA = g[4]; yD = g[7];
                     t = tn;
 #pragma unroll
-                    for (int k = 0; k < 12; k++) g[k] = gn[k];
+                    for (int k = 0; k < 8; k++) g[k] = gn[k];
                     ii = in;
                 }
                 if (cur != kRowInvalid) {

@@ -336,7 +336,7 @@ def test_full_size_properties(w, h, seed):
 def test_batch_equals_single_and_host_path():
     sb = _sb()
     torch = _torch()
-    w, h, nb = 640, 480, 5
+    w, h, nb = 640, 480, 9  # 9 frames: the host path pipelines them as chunks of 4 + 4 + 1
     frames = np.stack([sb.synth_frame(w, h, 100 + i) for i in range(nb)])
     det = make_det(w, h, 4, max_pts=4096, batch=nb)
     pitch = sb.iAlignUp(w, 128)
@@ -355,6 +355,12 @@ def test_batch_equals_single_and_host_path():
     hd = np.zeros((nb, 4096, 64), np.float32)
     det.detect_batch_host(frames, hp, hc, hd)
     assert np.array_equal(hc, counts)
+    # a second call reuses the streams and events; pinned buffers and a partial batch
+    hp2 = torch.zeros((nb, 4096 * 48), dtype=torch.uint8).pin_memory()
+    hc2 = torch.zeros(nb, dtype=torch.int32).pin_memory()
+    det.detect_batch_host(torch.from_numpy(frames).pin_memory()[:3], hp2, hc2, None)
+    assert np.array_equal(hc2.numpy()[:3], counts[:3])
+    assert np.array_equal(np.sort(hp2[1].numpy().view(sb.POINT_DTYPE)[: counts[1]]["x"]), np.sort(hp[1, : counts[1]]["x"]))
     single = make_det(w, h, 4, max_pts=4096)
     for f in range(nb):
         data, spts, sdesc = run_detect(single, frames[f], max_pts=4096)
