@@ -73,6 +73,26 @@ __device__ __forceinline__ int haar_x(const int* __restrict__ I, int ip, int x, 
     return box_sum(I, ip, x, x + s, y - s, y + s) - box_sum(I, ip, x - s, x, y - s, y + s);
 }
 
+// The geometry of one keypoint's sampling lattice (surfd.cu:1578-1590), shared by both descriptor kernels.
+struct KpGeom {
+    float fx, fy, spacing;
+    int ixc, iyc, step, S, R, side, e;
+};
+__device__ __forceinline__ KpGeom kp_geom(float x, float y, float scale, int W, int mag_factor) {
+    KpGeom g;
+    const float sc = __fmul_rn(1.65f, scale);
+    g.step = max(__float2int_rn(__fmul_rn(sc, 0.5f)), 1);
+    g.ixc = __float2int_rn(x);
+    g.iyc = __float2int_rn(y);
+    g.fx = __fsub_rn(x, __int2float_rn(g.ixc));
+    g.fy = __fsub_rn(y, __int2float_rn(g.iyc));
+    g.spacing = __fmul_rn(sc, __int2float_rn(mag_factor));
+    g.S = __float2int_rz(sc);
+    g.R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(g.spacing, __int2float_rn(W + 1)), 0.5f), __int2float_rn(g.step)));
+    g.side = 2 * g.R + 1;
+    g.e = 2 * g.step - g.S;
+    return g;
+}
 // launchers (one translation unit per stage)
 cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
                             int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);

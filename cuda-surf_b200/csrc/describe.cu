@@ -378,16 +378,12 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     const int half = lane >> 4, jl = lane & 15;
 
     for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
-        for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
         const float x = pts[pi].x, y = pts[pi].y;
-        const float sc = __fmul_rn(1.65f, pts[pi].scale);
-        const int step = max(__float2int_rn(__fmul_rn(sc, 0.5f)), 1);
-        const int ixc = __float2int_rn(x), iyc = __float2int_rn(y);
-        const float fx = __fsub_rn(x, __int2float_rn(ixc)), fy = __fsub_rn(y, __int2float_rn(iyc));
-        const float spacing = __fmul_rn(sc, __int2float_rn(P.mag_factor));
-        const int S = __float2int_rz(sc);
+        const KpGeom kg = kp_geom(x, y, pts[pi].scale, W, P.mag_factor);
+        for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
+        const int step = kg.step, ixc = kg.ixc, iyc = kg.iyc, S = kg.S, R = kg.R;
+        const float fx = kg.fx, fy = kg.fy, spacing = kg.spacing;
         const float wofs = __fmaf_rn(fW, 0.5f, -0.5f);
-        const int R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(spacing, __int2float_rn(W + 1)), 0.5f), __int2float_rn(step)));
         const int side = min(2 * R + 1, kRowTab);
         // per-row table (same IEEE operations as the reference's per-sample arithmetic). Valid rows
         // (inside the descriptor window and the image) form one contiguous range [row_lo, row_hi).

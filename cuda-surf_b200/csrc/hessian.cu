@@ -79,9 +79,13 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, f
     float* Rf = Rbase + (size_t)f * P.rstride;
     const int cx = q.delta * ix, cy = q.delta * iy;
     const int ms = P.max_scale;
-    for (int i = 0; i < q.nl; i++) {
+    // blockIdx.z is the computed layer: the octaves this kernel handles are small and their gathers are L2-latency
+    // bound, so the layers run as separate CTAs instead of a serial loop per thread
+    const int i = blockIdx.z;
+    if (i >= q.nl) return;
+    {
         const int b = q.b1[i];
-        if (ix < b || ix >= q.sw - b || iy < b || iy >= q.sh - b) continue;
+        if (ix < b || ix >= q.sw - b || iy < b || iy >= q.sh - b) return;
         const float v = hessian_response(I, P.ip, cx, cy, q.l[i], q.norm[i]);
         int s = q.s0 + i;
         Rf[q.resp_off + (size_t)s * q.osz + (size_t)iy * q.sp + ix] = v;
@@ -208,7 +212,11 @@ cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, f
         first_tile = P.noctaves > 1 ? P.oct[1].hess_tile0 : P.hess_tiles;
     }
     if (P.hess_tiles - first_tile > 0) {
-        const dim3 grid(P.hess_tiles - first_tile, nframes), block(32, 8);
+        int maxnl = 0;
+        for (int o = 0; o < P.noctaves; o++)
+            if (P.oct[o].hess_tile0 >= first_tile && P.oct[o].nl > maxnl) maxnl = P.oct[o].nl;
+        // (grid.y is the frame: the integral / response slots are indexed by blockIdx.y in every kernel)
+        const dim3 grid(P.hess_tiles - first_tile, nframes, maxnl), block(32, 8);
         hessian_kernel<<<grid, block, 0, st>>>(P, d_integral, d_resp, first_tile);
     }
     return cudaGetLastError();
