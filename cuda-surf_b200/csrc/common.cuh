@@ -47,6 +47,7 @@ struct PipeP {
     float thresh, divisor;
     int init_lobe, max_scale, noctaves, sampling;
     int upright, extend, desc_wsz, mag_factor, orient_size, nfeatures;
+    int doubled;              // 1: w, h, iw, ih describe the 2x up-sampled frame (surf.cpp:69-72, 234-235)
     int max_pts;
     int hess_tiles, nms_tiles;  // total linear tiles per frame
     OctaveP oct[kMaxOctave];
@@ -78,9 +79,11 @@ struct KpGeom {
     float fx, fy, spacing;
     int ixc, iyc, step, S, R, side, e;
 };
-__device__ __forceinline__ KpGeom kp_geom(float x, float y, float scale, int W, int mag_factor) {
+// doubled: the descriptor is sampled on the 2x image at (2x, 2y) with 3.3*scale (surfd.cu:1581-1592)
+__device__ __forceinline__ KpGeom kp_geom(float x, float y, float scale, int W, int mag_factor, int doubled) {
     KpGeom g;
-    const float sc = __fmul_rn(1.65f, scale);
+    if (doubled) { x = __fadd_rn(x, x); y = __fadd_rn(y, y); }
+    const float sc = __fmul_rn(doubled ? 3.3f : 1.65f, scale);
     g.step = max(__float2int_rn(__fmul_rn(sc, 0.5f)), 1);
     g.ixc = __float2int_rn(x);
     g.iyc = __float2int_rn(y);
@@ -94,6 +97,8 @@ __device__ __forceinline__ KpGeom kp_geom(float x, float y, float scale, int W, 
     return g;
 }
 // launchers (one translation unit per stage)
+cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_pitch, int w, int h, uint8_t* d_dst,
+                              size_t dst_stride, int dst_pitch, int nframes, cudaStream_t st);
 cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
                             int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);
 cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, float* d_resp, cudaStream_t st);

@@ -37,6 +37,8 @@ struct sb_ctx {
     float* d_resp = nullptr;
     int *d_colsum = nullptr, *d_rowsum = nullptr, *d_tilesum = nullptr;
     int* d_counts = nullptr;
+    uint8_t* d_up = nullptr;  // doubled=true: the 2x up-sampled frames, `batch` slots of up_pitch * P.h bytes
+    int up_pitch = 0;
     // staging for the synchronous / host-buffer entry points
     uint8_t* d_stage_img = nullptr;
     sb_point* d_stage_pts = nullptr;
@@ -68,17 +70,19 @@ static int align_up(int a, int b) { return (a % b) ? a - a % b + b : a; }
 static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
     if (p.width < 32 || p.height < 32) { why = "frame smaller than 32x32"; return SB_ERR_INVALID; }
     if (p.noctaves < 1 || p.noctaves > kMaxOctave) { why = "noctaves must be 1..8"; return SB_ERR_INVALID; }
-    if (p.doubled) { why = "doubled=true (2x up-sampled integral, surfd.cu:168-318) is not built yet"; return SB_ERR_UNSUPPORTED; }
     if (p.sampling_step < 1 || p.desc_wsz < 1 || p.desc_wsz > 4 || 12 % p.desc_wsz) { why = "sampling_step>=1, desc_wsz in {1,2,3,4}"; return SB_ERR_INVALID; }
     if (p.max_pts < 1 || p.batch < 1) { why = "max_pts and batch must be >= 1"; return SB_ERR_INVALID; }
-    if ((long long)p.width * p.height * 255 > 2147483647LL) { why = "frame too large for an int32 integral image"; return SB_ERR_INVALID; }
+    // doubled=true: the pipeline runs on the (2w-2) x (2h-2) up-sampled frame (surf.cpp:234-235, 377-378)
+    const int ew = p.doubled ? 2 * p.width - 2 : p.width, eh = p.doubled ? 2 * p.height - 2 : p.height;
+    if ((long long)ew * eh * 255 > 2147483647LL) { why = "frame too large for an int32 integral image"; return SB_ERR_INVALID; }
     std::memset(&P, 0, sizeof(P));
     // SurfParam, surf.cpp:66-79
-    P.divisor = 1.f;
+    P.doubled = p.doubled ? 1 : 0;
+    P.divisor = p.doubled ? 0.5f : 1.f;
     P.init_lobe = p.init_mask_size / 3;
     P.max_scale = P.init_lobe + 2;
     P.noctaves = p.noctaves;
-    P.sampling = p.sampling_step;
+    P.sampling = p.sampling_step + (p.doubled ? p.sampling_step : 0);
     P.thresh = p.thresh;
     P.upright = p.upright ? 1 : 0;
     P.extend = p.extend ? 1 : 0;
@@ -89,8 +93,8 @@ static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
     P.max_pts = p.max_pts;
     if (P.init_lobe < 1 || P.max_scale < 3 || P.max_scale > kMaxScale) { why = "init_mask_size must give 3..8 layers per octave"; return SB_ERR_INVALID; }
     // geometry, surf.cpp:377-390
-    P.w = p.width; P.h = p.height;
-    P.iw = p.width + 1; P.ih = p.height + 1; P.ip = align_up(P.iw, 128);
+    P.w = ew; P.h = eh;
+    P.iw = ew + 1; P.ih = eh + 1; P.ip = align_up(P.iw, 128);
     P.istride = (long long)P.ip * (P.ih + 2);  // one zero guard row above and below
     P.band_rows = 32;
     P.nbands = (P.h + 31) / 32;
@@ -163,7 +167,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_integral); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
-    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_stage_img); cudaFree(ctx->d_stage_pts);
+    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_stage_img); cudaFree(ctx->d_stage_pts);
     cudaFree(ctx->d_stage_desc);
     free_match_scratch(ctx->match_ws);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -212,6 +216,10 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     ok(cudaMalloc((void**)&c->d_rowsum, rowsz));
     ok(cudaMalloc((void**)&c->d_tilesum, ttsz));
     ok(cudaMalloc((void**)&c->d_counts, sizeof(int) * B));
+    if (P.doubled) {
+        c->up_pitch = align_up(P.w, 128);
+        ok(cudaMalloc((void**)&c->d_up, (size_t)c->up_pitch * P.h * B));
+    }
     ok(cudaMallocHost((void**)&c->h_counts, sizeof(int) * B));
     ok(cudaMallocHost((void**)&c->h_pts, sizeof(sb_point) * (size_t)P.max_pts));
     if (e == cudaSuccess) {
@@ -262,6 +270,13 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
     int* tilesum = ctx->d_tilesum + (size_t)slot0 * P.nbands * P.nchunks;
     CU(cudaMemsetAsync(d_counts, 0, sizeof(int) * nframes, st));
     if (ev) CU(cudaEventRecord(ev[0], st));
+    if (P.doubled) {
+        // the 2x frame replaces the caller's as the input of the integral stage
+        const size_t ustride = (size_t)ctx->up_pitch * P.h;
+        uint8_t* up = ctx->d_up + (size_t)slot0 * ustride;
+        CU(launch_upsample2x(d_images, image_stride, pitch, ctx->prm.width, ctx->prm.height, up, ustride, ctx->up_pitch, nframes, st));
+        d_images = up; image_stride = ustride; pitch = ctx->up_pitch;
+    }
     CU(launch_integral(P, d_images, image_stride, pitch, nframes, integral, colsum, rowsum, tilesum, st));
     if (ev) CU(cudaEventRecord(ev[1], st));
     CU(launch_hessian(P, nframes, integral, resp, st));
@@ -279,7 +294,7 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
 extern "C" int sb_detect_batch_profile(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
                                        sb_point* d_points, int* d_counts, float* d_desc, void* stream, float* stage_ms) {
     if (!ctx) return SB_ERR_INVALID;
-    if (!d_images || !d_points || !d_counts || !stage_ms || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->P.w)
+    if (!d_images || !d_points || !d_counts || !stage_ms || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->prm.width)
         return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_profile: bad argument");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -298,7 +313,7 @@ extern "C" int sb_detect_batch_profile(sb_ctx* ctx, const uint8_t* d_images, siz
 extern "C" int sb_detect_batch_async(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
                                      sb_point* d_points, int* d_counts, float* d_desc, void* stream) {
     if (!ctx) return SB_ERR_INVALID;
-    if (!d_images || !d_points || !d_counts || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->P.w)
+    if (!d_images || !d_points || !d_counts || nframes < 1 || nframes > ctx->prm.batch || pitch < ctx->prm.width)
         return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_async: bad argument (nframes must be 1..batch, pitch >= width)");
     CU(cudaSetDevice(ctx->device));
     // `stream` is used literally: NULL is the CUDA default stream, as for any CUDA API
@@ -316,7 +331,7 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
     if (!ctx) return SB_ERR_INVALID;
     const PipeP& P = ctx->P;
     if (!d_image || !d_points || !num_pts) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: null argument");
-    if (w != P.w || h != P.h) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: frame size differs from the context's (create one context per size)");
+    if (w != ctx->prm.width || h != ctx->prm.height) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: frame size differs from the context's (create one context per size)");
     if (max_pts != P.max_pts) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: max_pts differs from the context's");
     if (pitch < w) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: pitch < width");
     CU(cudaSetDevice(ctx->device));
@@ -356,9 +371,10 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
         return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_host: bad argument");
     CU(cudaSetDevice(ctx->device));
     const int B = ctx->prm.batch;
-    const size_t fbytes = (size_t)P.w * P.h;
-    const int dpitch = align_up(P.w, 128);
-    const size_t dstride = (size_t)dpitch * P.h;
+    const int sw_ = ctx->prm.width, sh_ = ctx->prm.height;  // the caller's frame size (P.w, P.h are the 2x size if doubled)
+    const size_t fbytes = (size_t)sw_ * sh_;
+    const int dpitch = align_up(sw_, 128);
+    const size_t dstride = (size_t)dpitch * sh_;
     if (!ctx->d_stage_img) {
         CU(cudaMalloc((void**)&ctx->d_stage_img, dstride * B));
         CU(cudaMemset(ctx->d_stage_img, 0, dstride * B));
@@ -388,11 +404,11 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
     const size_t pstride = (size_t)P.max_pts, dstride_f = (size_t)P.max_pts * P.nfeatures;
     for (int k = 0; k < nchunks; k++) {
         const int f0 = k * chunk, nf = std::min(chunk, nframes - f0);
-        if (dpitch == P.w) {
+        if (dpitch == sw_) {
             CU(cudaMemcpyAsync(ctx->d_stage_img + f0 * dstride, h_images + f0 * fbytes, fbytes * nf, cudaMemcpyHostToDevice, ctx->s_h2d));
         } else {
             for (int f = f0; f < f0 + nf; f++)
-                CU(cudaMemcpy2DAsync(ctx->d_stage_img + f * dstride, dpitch, h_images + f * fbytes, P.w, P.w, P.h,
+                CU(cudaMemcpy2DAsync(ctx->d_stage_img + f * dstride, dpitch, h_images + f * fbytes, sw_, sw_, sh_,
                                      cudaMemcpyHostToDevice, ctx->s_h2d));
         }
         CU(cudaEventRecord(ctx->ev_in[k], ctx->s_h2d));

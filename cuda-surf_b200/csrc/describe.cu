@@ -75,7 +75,8 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
     OrientSmem& S = sm[warp];
 
     for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
-        const float x = pts[pi].x, y = pts[pi].y, scale = pts[pi].scale;
+        float x = pts[pi].x, y = pts[pi].y, scale = pts[pi].scale;
+        if (P.doubled) { x = __fadd_rn(x, x); y = __fadd_rn(y, y); scale = __fadd_rn(scale, scale); }  // surfd.cu:1734-1739
         const int hs = __float2int_rz(__fmaf_rn(2.f, scale, 1.6f));
         const int st = __float2int_rz(__fadd_rn(scale, 0.8f));
         const int ixc = __float2int_rn(x), iyc = __float2int_rn(y);
@@ -242,8 +243,9 @@ describe_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, 
 
     for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
         for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
-        const float x = pts[pi].x, y = pts[pi].y;
-        const float sc = __fmul_rn(1.65f, pts[pi].scale);
+        float x = pts[pi].x, y = pts[pi].y;
+        if (P.doubled) { x = __fadd_rn(x, x); y = __fadd_rn(y, y); }  // surfd.cu:2406-2411
+        const float sc = __fmul_rn(P.doubled ? 3.3f : 1.65f, pts[pi].scale);
         const int step = max(__float2int_rn(__fmul_rn(sc, 0.5f)), 1);
         const int ixc = __float2int_rn(x), iyc = __float2int_rn(y);
         const float fx = __fsub_rn(x, __int2float_rn(ixc)), fy = __fsub_rn(y, __int2float_rn(iyc));
@@ -379,7 +381,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
 
     for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
         const float x = pts[pi].x, y = pts[pi].y;
-        const KpGeom kg = kp_geom(x, y, pts[pi].scale, W, P.mag_factor);
+        const KpGeom kg = kp_geom(x, y, pts[pi].scale, W, P.mag_factor, P.doubled);
         for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
         const int step = kg.step, ixc = kg.ixc, iyc = kg.iyc, S = kg.S, R = kg.R;
         const float fx = kg.fx, fy = kg.fy, spacing = kg.spacing;

@@ -185,6 +185,52 @@ integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs,
     }
 }
 
+// ------------------------------------------------------------------ doubled=true: 2x up-sampling
+//
+// The reference builds the integral of a 2x bilinear up-sampling of the frame (integralDoubleRow0U2 + five scan
+// kernels, surfd.cu:166-318, 2707-2772). The up-sampled pixels are defined by surfd.cu:182-206: even/even the source
+// pixel, otherwise rn() of the mean of the 2 or 4 neighbours; the image the scans cover is (2w-2) x (2h-2). Here the
+// 2x image is materialised as u8 (one thread per 4 output pixels, 32-bit stores) and goes through the same
+// reduce-then-scan kernels as any frame.
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint8_t* __restrict__ src, size_t src_stride, int src_pitch, int w, int h, uint8_t* __restrict__ dst,
+                  size_t dst_stride, int dst_pitch) {
+    const int W2 = 2 * w - 2, H2 = 2 * h - 2;
+    const int X = 4 * (blockIdx.x * blockDim.x + threadIdx.x), Y = blockIdx.y;
+    if (X >= W2 || Y >= H2) return;
+    const uint8_t* r0 = src + blockIdx.z * src_stride + (size_t)(Y >> 1) * src_pitch + (X >> 1);
+    const uint8_t* r1 = (Y & 1) ? r0 + src_pitch : r0;  // odd rows average two source rows
+    // source columns x, x+1, x+2 (x+2 only feeds output X+3, which exists iff X+3 < W2)
+    const int a0 = r0[0] + r1[0], a1 = r0[1] + r1[1];
+    const int a2 = (X + 3 < W2) ? r0[2] + r1[2] : a1;
+    unsigned v[4];
+    if (Y & 1) {
+        v[0] = __float2int_rn(__int2float_rn(a0) * 0.5f);
+        v[1] = __float2int_rn(__int2float_rn(a0 + a1) * 0.25f);
+        v[2] = __float2int_rn(__int2float_rn(a1) * 0.5f);
+        v[3] = __float2int_rn(__int2float_rn(a1 + a2) * 0.25f);
+    } else {  // r1 == r0: a = 2 * pixel
+        v[0] = a0 >> 1;
+        v[1] = __float2int_rn(__int2float_rn((a0 + a1) >> 1) * 0.5f);
+        v[2] = a1 >> 1;
+        v[3] = __float2int_rn(__int2float_rn((a1 + a2) >> 1) * 0.5f);
+    }
+    uint8_t* d = dst + blockIdx.z * dst_stride + (size_t)Y * dst_pitch + X;
+    if (X + 3 < W2) {
+        *reinterpret_cast<unsigned*>(d) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+    } else {
+        for (int k = 0; k < 4 && X + k < W2; k++) d[k] = (uint8_t)v[k];
+    }
+}
+
+cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_pitch, int w, int h, uint8_t* d_dst,
+                              size_t dst_stride, int dst_pitch, int nframes, cudaStream_t st) {
+    const int W2 = 2 * w - 2, H2 = 2 * h - 2;
+    const dim3 grid((W2 / 4 + 256) / 256, H2, nframes), block(256);
+    upsample2x_kernel<<<grid, block, 0, st>>>(d_src, src_stride, src_pitch, w, h, d_dst, dst_stride, dst_pitch);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
                             int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st) {
     const dim3 grid(P.nchunks, P.nbands, nframes), block(kThreads);

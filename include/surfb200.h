@@ -27,7 +27,7 @@ typedef enum {
     SB_OK = 0,
     SB_ERR_INVALID = -1,     /* bad argument */
     SB_ERR_CUDA = -2,        /* CUDA runtime / launch failure, or no usable device */
-    SB_ERR_UNSUPPORTED = -3, /* valid reference configuration not built yet (doubled=true) */
+    SB_ERR_UNSUPPORTED = -3, /* valid reference configuration this library does not build */
     SB_ERR_NOMEM = -4
 } sb_status;
 
@@ -49,7 +49,7 @@ typedef struct sb_point {
 typedef struct sb_params {
     int noctaves;       /* _noctaves                                            */
     float thresh;       /* _thresh                                              */
-    int doubled;        /* _doubled      (1 -> SB_ERR_UNSUPPORTED this round)   */
+    int doubled;        /* _doubled: run on the 2x up-sampled frame              */
     int init_mask_size; /* _init_mask_size (9 -> lobe 3, 5 layers per octave)   */
     int sampling_step;  /* _sampling_step                                       */
     int upright;        /* _upright                                             */
@@ -64,7 +64,7 @@ typedef struct sb_params {
 /* Derived geometry (surf.cpp:374-390), for callers that size buffers. */
 typedef struct sb_info {
     int max_scale, nfeatures;
-    int iw, ih, ipitch;        /* integral image (w+1, h+1, pitch in ints)       */
+    int iw, ih, ipitch;        /* integral image (w+1, h+1; 2w-1, 2h-1 if doubled; pitch in ints) */
     int sw[8], sh[8], sp[8];   /* per-octave response dims and pitch             */
     long long resp_floats;     /* tight floats per frame: sum max_scale*sw*sh    */
     int kernels_per_frame;     /* launches per detect+describe pass              */

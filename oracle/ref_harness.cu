@@ -75,8 +75,9 @@ void* ref_create(int device, int noctaves, float thresh, int doubled, int init_m
     H->det = new Surfor;
     H->det->init(noctaves, thresh, doubled != 0, init_mask_size, sampling_step, upright != 0, extend != 0, desc_wsz,
                  width, height);
-    CHECK(cudaMalloc((void**)&H->d_img, (size_t)H->pitch * height));
-    CHECK(cudaMemset(H->d_img, 0, (size_t)H->pitch * height));
+    // two spare rows: with doubled=true integralDoubleRow0U2 reads one row past the frame (surfd.cu:172-184)
+    CHECK(cudaMalloc((void**)&H->d_img, (size_t)H->pitch * (height + 2)));
+    CHECK(cudaMemset(H->d_img, 0, (size_t)H->pitch * (height + 2)));
     return H;
 }
 
@@ -145,16 +146,17 @@ int ref_match(void* h, SurfPoint* pts1, int n1, const float* desc1, const SurfPo
 // Returns total floats written to out_resp (or the required count when out_resp==NULL).
 long long ref_stages(void* h, const uint8_t* img, int32_t* out_integral, float* out_resp, int* out_dims) {
     RefHandle* H = (RefHandle*)h;
-    if (H->doubled) return -1;
     upload(H, img);
     const int init_lobe = H->init_mask / 3;
     const int max_scale = init_lobe + 2;
     const int noct = H->noctaves;
+    const int sampling = H->doubled ? 2 * H->sampling : H->sampling;  // surf.cpp:72
     int3 whp0 = make_int3(H->w, H->h, H->pitch);
-    int3 iwhp = make_int3(H->w + 1, H->h + 1, iAlignUp(H->w + 1, 128));
+    int3 iwhp = H->doubled ? make_int3(2 * H->w - 1, 2 * H->h - 1, iAlignUp(2 * H->w - 1, 128))   // surf.cpp:377-379
+                           : make_int3(H->w + 1, H->h + 1, iAlignUp(H->w + 1, 128));
     int3 swhps[MAX_OCTAVE];
     int osizes[MAX_OCTAVE];
-    swhps[0] = make_int3((iwhp.x - 1) / H->sampling, (iwhp.y - 1) / H->sampling, 0);
+    swhps[0] = make_int3((iwhp.x - 1) / sampling, (iwhp.y - 1) / sampling, 0);
     swhps[0].z = iAlignUp(swhps[0].x, 128);
     osizes[0] = swhps[0].y * swhps[0].z;
     long long tot = (long long)osizes[0] * max_scale;
@@ -170,25 +172,27 @@ long long ref_stages(void* h, const uint8_t* img, int32_t* out_integral, float* 
     if (!out_resp && !out_integral) return tight;
 
     int* iimage = nullptr; float* tmem = nullptr;
-    CHECK(cudaMalloc((void**)&iimage, sizeof(int) * (size_t)iwhp.z * iwhp.y));
-    CHECK(cudaMemset(iimage, 0, sizeof(int) * (size_t)iwhp.z * iwhp.y));
+    // four spare rows: the doubled row kernel writes rows 2h-1 and 2h of a (2h-1)-row image (surfd.cu:180-206)
+    CHECK(cudaMalloc((void**)&iimage, sizeof(int) * (size_t)iwhp.z * (iwhp.y + 4)));
+    CHECK(cudaMemset(iimage, 0, sizeof(int) * (size_t)iwhp.z * (iwhp.y + 4)));
     CHECK(cudaMalloc((void**)&tmem, sizeof(float) * tot));
     CHECK(cudaMemset(tmem, 0, sizeof(float) * tot));
 
-    cuIntegral(H->d_img, iimage, whp0, iwhp);
+    if (H->doubled) cuIntegralDoubleU4(H->d_img, iimage, whp0, iwhp);
+    else cuIntegral(H->d_img, iimage, whp0, iwhp);
     int mask_size = init_lobe - 2, s = 0, octave = 1, border1 = 0, offset = 0;
     int borders[MAX_OCTAVE];
     for (int o = 0; o < noct; o++) {
         if (o > 0) {
             cuHalfImage(tmem + offset - 3 * osizes[o - 1], tmem + offset, swhps[o - 1], swhps[o]);
             cuHalfImage(tmem + offset - 1 * osizes[o - 1], tmem + offset + osizes[o], swhps[o - 1], swhps[o]);
-            border1 = ((3 * (mask_size + 4 * octave)) / 2) / (H->sampling * octave) + 1;
+            border1 = ((3 * (mask_size + 4 * octave)) / 2) / (sampling * octave) + 1;
             borders[0] = border1; borders[1] = border1; s = 2;
         } else {
-            border1 = ((3 * (mask_size + 6 * octave)) / 2) / (H->sampling * octave) + 1;
+            border1 = ((3 * (mask_size + 6 * octave)) / 2) / (sampling * octave) + 1;
         }
         cuCalcHessianMulti(iimage, tmem + offset, iwhp, swhps[o], s, max_scale, mask_size, border1, borders, octave,
-                           H->sampling);
+                           sampling);
         offset += max_scale * osizes[o];
         octave += octave;
     }

@@ -58,7 +58,8 @@ void or_make_params(or_params* p, int noctaves, float thresh, int doubled, int i
 /* Geometry: surf.cpp:374-390. Octave loop: surf.cpp:240-294. Per-layer parameters:
  * surfd.cu:2844-2865. NMS borders: surfd.cu:3062-3073. Returns 0, or -1 for unsupported. */
 int or_make_schedule(const or_params* p, int w, int h, or_octave* sched) {
-    if (p->doubled || p->max_scale > OR_MAX_SCALE || p->noctaves > OR_MAX_OCTAVE) return -1;
+    /* doubled: w, h are the dimensions of the 2x image (2*W-2, 2*H-2), see or_upsample2x */
+    if (p->max_scale > OR_MAX_SCALE || p->noctaves > OR_MAX_OCTAVE) return -1;
     int iw = w + 1, ih = h + 1;
     int sw = (iw - 1) / p->sampling, sh = (ih - 1) / p->sampling;
     int mask = p->init_lobe - 2, octave = 1, s = 0, border1 = 0;
@@ -124,6 +125,38 @@ void or_integral(const uint8_t* img, int w, int h, int pitch, int32_t* out) {
             row[x + 1] = run + up[x + 1];
         }
     }
+}
+
+/* doubled=true (surf.cpp:234-235): the integral image is that of a 2x bilinear up-sampling of the frame.
+ * integralDoubleRow0U2 (surfd.cu:166-207) defines the up-sampled pixels -- even/even: the source pixel;
+ * even row, odd column: rn((a+b)*0.5f) of the horizontal neighbours; odd row, even column: the same of
+ * the vertical neighbours; odd/odd: rn((a+b+c+d)*0.25f) -- and the scan kernels (surfd.cu:209-318,
+ * 2707-2772) sum columns 1..2W-2 and rows 1..2H-2 of the padded layout, i.e. the 2x image is
+ * (2W-2) x (2H-2): its last row / column would need source pixels outside the frame (the reference reads
+ * and writes out of bounds there, outside the region every later stage uses). */
+void or_upsample2x(const uint8_t* img, int w, int h, int pitch, uint8_t* out) {
+    const int W2 = 2 * w - 2, H2 = 2 * h - 2;
+    for (int Y = 0; Y < H2; Y++) {
+        const uint8_t* r0 = img + (size_t)(Y >> 1) * pitch;
+        const uint8_t* r1 = r0 + pitch;
+        uint8_t* d = out + (size_t)Y * W2;
+        for (int X = 0; X < W2; X++) {
+            const int x = X >> 1;
+            int v;
+            if (!(Y & 1)) v = (X & 1) ? f2i_rn((float)(r0[x] + r0[x + 1]) * 0.5f) : r0[x];
+            else v = (X & 1) ? f2i_rn((float)(r0[x] + r0[x + 1] + r1[x] + r1[x + 1]) * 0.25f) : f2i_rn((float)(r0[x] + r1[x]) * 0.5f);
+            d[X] = (uint8_t)v;
+        }
+    }
+}
+
+/* out: tight (2h-1) x (2w-1) */
+void or_integral_doubled(const uint8_t* img, int w, int h, int pitch, int32_t* out) {
+    const int W2 = 2 * w - 2, H2 = 2 * h - 2;
+    uint8_t* up = (uint8_t*)malloc((size_t)W2 * H2);
+    or_upsample2x(img, w, h, pitch, up);
+    or_integral(up, W2, H2, W2, out);
+    free(up);
 }
 
 /* The reference indexes the integral with pitch iAlignUp(w+1,128) and can stray a few elements
@@ -627,10 +660,18 @@ void or_match(or_point* pts1, int n1, const float* f1, const or_point* pts2, int
 int or_detect_and_compute(const or_params* p, const uint8_t* img, int w, int h, int pitch, or_point* pts, int max_pts,
                           float* desc) {
     or_octave sched[OR_MAX_OCTAVE];
-    if (or_make_schedule(p, w, h, sched) != 0) return -1;
+    uint8_t* up = NULL;
+    if (p->doubled) { /* everything downstream runs on the 2x image (surf.cpp:234-235) */
+        if (w < 2 || h < 2) return -1;
+        up = (uint8_t*)malloc((size_t)(2 * w - 2) * (2 * h - 2));
+        or_upsample2x(img, w, h, pitch, up);
+        img = up; w = 2 * w - 2; h = 2 * h - 2; pitch = w;
+    }
+    if (or_make_schedule(p, w, h, sched) != 0) { free(up); return -1; }
     int32_t* I = (int32_t*)malloc(sizeof(int32_t) * (size_t)(w + 1) * (h + 1));
     float* resp = (float*)malloc(sizeof(float) * (size_t)or_resp_floats(p, sched));
     or_integral(img, w, h, pitch, I);
+    free(up);
     or_hessian(p, sched, I, w, h, resp);
     const int n = or_find_keypoints(p, sched, I, w, h, resp, pts, max_pts);
     if (desc) {

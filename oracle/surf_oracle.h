@@ -60,6 +60,8 @@ int or_make_schedule(const or_params* p, int w, int h, or_octave* sched /*[nocta
 long long or_resp_floats(const or_params* p, const or_octave* sched);
 
 /* integral: img tight pitch `pitch` bytes; out: (h+1) rows x (w+1) cols, tight. */
+void or_upsample2x(const uint8_t* img, int w, int h, int pitch, uint8_t* out /* (2h-2) x (2w-2) */);
+void or_integral_doubled(const uint8_t* img, int w, int h, int pitch, int32_t* out /* (2h-1) x (2w-1) */);
 void or_integral(const uint8_t* img, int w, int h, int pitch, int32_t* out);
 /* Hessian: integral tight (w+1)x(h+1); resp: per octave max_scale layers of sw*sh, concatenated. */
 void or_hessian(const or_params* p, const or_octave* sched, const int32_t* integral, int w, int h, float* resp);

@@ -58,6 +58,8 @@ def lib():
         L.or_resp_floats.argtypes = [C.POINTER(OrParams), C.POINTER(OrOctave)]
         L.or_resp_floats.restype = C.c_longlong
         L.or_integral.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+        L.or_integral_doubled.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+        L.or_integral_doubled.restype = None
         L.or_hessian.argtypes = [C.POINTER(OrParams), C.POINTER(OrOctave), vp, C.c_int, C.c_int, vp]
         L.or_find_keypoints.argtypes = [C.POINTER(OrParams), C.POINTER(OrOctave), vp, C.c_int, C.c_int, vp, vp, C.c_int]
         L.or_find_keypoints.restype = C.c_int
@@ -91,12 +93,16 @@ class Oracle:
         sched = (OrOctave * 8)()
         rc = lib().or_make_schedule(C.byref(self.p), w, h, sched)
         if rc != 0:
-            raise ValueError("unsupported parameters (doubled / too many scales or octaves)")
+            raise ValueError("unsupported parameters (too many scales or octaves)")
         return sched
 
     def integral(self, img):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         h, w = img.shape
+        if self.p.doubled:  # integral of the 2x up-sampled frame, (2h-1) x (2w-1)
+            out = np.empty((2 * h - 1, 2 * w - 1), np.int32)
+            lib().or_integral_doubled(_ptr(img), w, h, w, _ptr(out))
+            return out
         out = np.empty((h + 1, w + 1), np.int32)
         lib().or_integral(_ptr(img), w, h, w, _ptr(out))
         return out

@@ -51,6 +51,7 @@ class Reference:
                  extend=False, desc_wsz=4, device=0):
         self.w, self.h = w, h
         self.noctaves = noctaves
+        self.doubled = bool(doubled)
         self.max_scale = init_mask_size // 3 + 2
         self.nfeatures = desc_wsz * desc_wsz * (8 if extend else 4)
         self.hnd = lib().ref_create(device, noctaves, thresh, int(doubled), init_mask_size, sampling_step, int(upright),
@@ -74,7 +75,7 @@ class Reference:
         img = np.ascontiguousarray(img, np.uint8)
         dims = np.zeros(2 * self.noctaves, np.int32)
         n = lib().ref_stages(self.hnd, img.ctypes.data, None, None, dims.ctypes.data)
-        integral = np.zeros((self.h + 1, self.w + 1), np.int32)
+        integral = np.zeros((2 * self.h - 1, 2 * self.w - 1) if self.doubled else (self.h + 1, self.w + 1), np.int32)
         resp = np.zeros(n, np.float32)
         lib().ref_stages(self.hnd, img.ctypes.data, integral.ctypes.data, resp.ctypes.data, dims.ctypes.data)
         out, off = [], 0

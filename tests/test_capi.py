@@ -49,7 +49,7 @@ def test_create_fails_loudly_without_gpu():
 
 
 @pytest.mark.parametrize("kw,code", [
-    (dict(doubled=True), B.SB_ERR_UNSUPPORTED),       # next row
+    (dict(doubled=True, width=2100, height=2100), B.SB_ERR_INVALID),  # the 2x frame overflows an int32 integral
     (dict(noctaves=9), B.SB_ERR_INVALID),             # MAX_OCTAVE 8 (surfd.h:10)
     (dict(init_mask_size=21), B.SB_ERR_INVALID),      # lobe 7 -> 9 layers > MAX_SCALE 8 (surfd.h:9)
     (dict(width=16), B.SB_ERR_INVALID),

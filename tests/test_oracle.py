@@ -155,3 +155,43 @@ def test_oracle_match_against_reference_golden():
     assert np.array_equal(m["match"], want["match"])
     assert np.array_equal(m["score"], want["score"])
     assert np.allclose(m["ambiguity"], want["ambiguity"], atol=1e-6)
+
+
+def test_doubled_upsample_and_integral():
+    """doubled=true (surf.cpp:234-235): the integral is that of the (2w-2) x (2h-2) bilinear 2x frame defined by
+    integralDoubleRow0U2 (surfd.cu:166-207)."""
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    h, w = img.shape
+    orc = ol.Oracle(3, 4.0, True, 9, 2, True, False, 4)
+    I = orc.integral(img)
+    assert I.shape == (2 * h - 1, 2 * w - 1)
+    a = img.astype(np.float32)
+    up = np.zeros((2 * h - 2, 2 * w - 2), np.float32)
+    up[0::2, 0::2] = a[: h - 1, : w - 1]
+    up[0::2, 1::2] = np.rint((a[: h - 1, : w - 1] + a[: h - 1, 1:]) * np.float32(0.5))       # rint: ties to even, as cvt.rni
+    up[1::2, 0::2] = np.rint((a[: h - 1, : w - 1] + a[1:, : w - 1]) * np.float32(0.5))
+    up[1::2, 1::2] = np.rint((a[: h - 1, : w - 1] + a[: h - 1, 1:] + a[1:, : w - 1] + a[1:, 1:]) * np.float32(0.25))
+    want = np.zeros_like(I)
+    want[1:, 1:] = up.astype(np.int64).cumsum(0).cumsum(1)
+    assert np.array_equal(I, want)
+    # the whole path runs on the 2x frame: sampling doubles, positions and scales are halved back (surf.cpp:69-72)
+    assert orc.p.sampling == 4 and orc.p.divisor == 0.5
+
+
+def test_doubled_detect_is_consistent_with_plain_detect_on_the_2x_frame():
+    """Keypoints of doubled=true on a frame == keypoints of doubled=false with sampling 4 on the 2x frame, with
+    x, y, scale halved (makePoint, surfd.cu:1003-1006)."""
+    import cuda_surf_b200 as sb
+    img = sb.synth_frame(320, 240, 7)
+    h, w = img.shape
+    od = ol.Oracle(3, 4.0, True, 9, 2, True, False, 4)
+    pd, dd = od.detect_and_compute(img)
+    assert len(pd) > 50
+    I2 = od.integral(img)
+    op = ol.Oracle(3, 4.0, False, 9, 4, True, False, 4)
+    pp = op.keypoints(I2, op.hessian(I2))
+    assert len(pp) == len(pd)
+    assert np.allclose(np.sort(pp["x"]) * 0.5, np.sort(pd["x"]), atol=1e-5)
+    assert np.allclose(np.sort(pp["scale"]) * 0.5, np.sort(pd["scale"]), atol=1e-5)
+    assert np.allclose(np.linalg.norm(dd, axis=1), 1.0, atol=1e-4)

@@ -30,10 +30,10 @@ def _sb():
     return sb
 
 
-def make_det(w, h, noctaves=4, thresh=4.0, upright=True, extend=False, max_pts=32768, batch=1):
+def make_det(w, h, noctaves=4, thresh=4.0, upright=True, extend=False, max_pts=32768, batch=1, doubled=False):
     sb = _sb()
     det = sb.Surfor()
-    det.init(noctaves, thresh, False, 9, 2, upright, extend, 4, w, h, max_pts=max_pts, batch=batch)
+    det.init(noctaves, thresh, doubled, 9, 2, upright, extend, 4, w, h, max_pts=max_pts, batch=batch)
     return det
 
 
@@ -401,3 +401,45 @@ def test_edge_cases():
     d_img, whp = upload(sb.synth_frame(100, 96, 1))
     with pytest.raises(sb.SurfError):
         det.detectAndCompute(d_img, sb.initSurfData(64), whp)
+
+
+# ---------------------------------------------------------------------------------------- doubled=true
+
+@pytest.mark.parametrize("w,h,upright", [(640, 480, True), (333, 251, False)])
+def test_doubled_vs_oracle(w, h, upright):
+    """Surfor::init(..., doubled=true): integral of the 2x frame and Hessian maps bit-exact, keypoints / descriptors
+    as for the plain path."""
+    sb = _sb()
+    img = sb.synth_frame(w, h, 21)
+    det = make_det(w, h, 3, upright=upright, doubled=True)
+    orc = ol.Oracle(3, 4.0, True, 9, 2, upright, False, 4)
+    data, pts, desc = run_detect(det, img)
+    I = det.get_integral()
+    Iw = orc.integral(img)
+    assert I.shape == (2 * h - 1, 2 * w - 1) and np.array_equal(I, Iw)
+    assert np.array_equal(det.get_response().view(np.uint32), orc.hessian(Iw).view(np.uint32))
+    opts, odesc = orc.detect_and_compute(img)
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(opts, pts)
+    assert len(opts) > 100 and fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\n{describe_misses(miss_r, 4.0)}"
+    l2 = np.linalg.norm(desc[idx[ok]] - odesc[ok], axis=1)
+    assert (l2 <= (1e-3 if upright else 5e-3)).mean() >= 0.99, f"descriptor L2 max {l2.max():.3e}"
+
+
+@REF
+def test_doubled_vs_reference():
+    """The reference's own doubled path (cuIntegralDoubleU4 + the same pipeline), stage dump and public API."""
+    sb = _sb()
+    w, h = 640, 480
+    img = sb.synth_frame(w, h, 22)
+    ref = ref_lib.Reference(w, h, 3, 4.0, True, 9, 2, True, False, 4)
+    rI, rresp, rflat = ref.stages(img)
+    rpts, rdesc = ref.detect(img)
+    ref.close()
+    det = make_det(w, h, 3, doubled=True)
+    data, pts, desc = run_detect(det, img)
+    assert np.array_equal(det.get_integral(), rI), "integral of the 2x frame differs from cuIntegralDoubleU4"
+    assert np.array_equal(det.get_response().view(np.uint32), rflat.view(np.uint32))
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(rpts, pts)
+    assert len(rpts) > 100 and fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\n{describe_misses(miss_r, 4.0)}"
+    l2 = np.linalg.norm(desc[idx[ok]] - rdesc[ok], axis=1)
+    assert (l2 <= 1e-3).mean() >= 0.99, f"descriptor L2 max {l2.max():.3e}"
