@@ -116,5 +116,7 @@ struct MatchScratch {
 cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
                          int nfeatures, MatchScratch& ws, int sm_count, cudaStream_t st);
 void free_match_scratch(MatchScratch& ws);
+cudaError_t launch_match_filter(const sb_point* d_pts1, int n1, const sb_point* d_pts2, int n2, float max_ambiguity, int flags,
+                                sb_pair* d_pairs, int cap, int* d_count, cudaStream_t st);
 
 }  // namespace sb

@@ -485,6 +485,25 @@ extern "C" int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1,
     return SB_OK;
 }
 
+extern "C" int sb_match_filter(sb_ctx* ctx, const sb_point* d_pts1, int n1, const sb_point* d_pts2, int n2, float max_ambiguity,
+                               int flags, sb_pair* d_pairs, sb_pair* h_pairs, int cap, int* num_pairs) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (!num_pairs || n1 < 0 || n2 < 0 || cap < 0 || (n1 > 0 && (!d_pts1 || !d_pairs)) ||
+        ((flags & (SB_FILTER_LAPLACE | SB_FILTER_CROSS)) && n1 > 0 && !d_pts2))
+        return fail(ctx, SB_ERR_INVALID, "sb_match_filter: bad argument");
+    *num_pairs = 0;
+    if (n1 == 0 || cap == 0) return SB_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(launch_match_filter(d_pts1, n1, d_pts2, n2, max_ambiguity, flags, d_pairs, cap, ctx->d_counts, st));
+    CU(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int n = ctx->h_counts[0];
+    *num_pairs = n;
+    if (h_pairs && n > 0) CU(cudaMemcpy(h_pairs, d_pairs, sizeof(sb_pair) * (size_t)n, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
 extern "C" int sb_get_integral(sb_ctx* ctx, int slot, int32_t* h_out) {
     if (!ctx || !h_out || slot < 0 || slot >= ctx->prm.batch) return SB_ERR_INVALID;
     const PipeP& P = ctx->P;

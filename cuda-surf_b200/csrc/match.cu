@@ -376,11 +376,8 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     match_prep<NF><<<((n1pad + n2pad) * NF + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a, d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b);
     CUtensorMap mapA, mapB;
     if (!make_map(&mapA, ws.a, n1pad, Cfg::KTOT, kBM) || !make_map(&mapB, ws.b, n2pad, Cfg::KTOT, Cfg::BN)) return cudaErrorNotSupported;
-    static bool attr_set = false;  // per template instance; the attribute is per function, not per context
-    if (!attr_set) {
-        if ((e = cudaFuncSetAttribute(match_mma<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // per device (a process may hold contexts on several GPUs), so set on every launch
+    if ((e = cudaFuncSetAttribute(match_mma<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
     match_mma<NF><<<dim3(rbs, nsplit), 256, Cfg::SMEM, st>>>(mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
     match_final<NF><<<(n1 + 3) / 4, 128, 0, st>>>(d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit * 2, n1pad);
     return cudaGetLastError();

@@ -124,6 +124,21 @@ class Surfor:
                                     data2.d_data.data_ptr(), data2.num_pts, features2.data_ptr(), C.c_void_p(st))
         B.check(rc, self._ctx)
 
+    def match_filter(self, data1, data2, max_ambiguity=0.8, laplace=False, cross=False):
+        """Pairs (idx1, idx2, score, ambiguity) of the rows of data1 accepted by the consumer-side ratio test
+        `ambiguity < max_ambiguity` (BASELINE config 5), optionally with equal Laplacian signs and a symmetric
+        cross-check (data2 must then hold the reverse match). Returns a numpy array of PAIR_DTYPE in row order."""
+        import torch
+        n1 = data1.num_pts
+        pairs = torch.zeros((max(n1, 1), 16), dtype=torch.uint8, device=data1.d_data.device)
+        host = np.zeros(max(n1, 1), B.PAIR_DTYPE)
+        n = C.c_int(0)
+        flags = (B.FILTER_LAPLACE if laplace else 0) | (B.FILTER_CROSS if cross else 0)
+        rc = B.lib().sb_match_filter(self._ctx, data1.d_data.data_ptr(), n1, data2.d_data.data_ptr(), data2.num_pts,
+                                     max_ambiguity, flags, pairs.data_ptr(), host.ctypes.data, n1, C.byref(n))
+        B.check(rc, self._ctx)
+        return host[: n.value].copy()
+
     # ---- batched forms (frame loop of main.cpp:239-245 without per-frame host round trips) ----------
     def detect_batch(self, images, pitch, points, counts, desc=None, stream=None):
         """images uint8 CUDA [n, h, pitch]; points uint8 CUDA [n, max_pts*48]; counts int32 CUDA [n];

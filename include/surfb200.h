@@ -105,6 +105,18 @@ int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const floa
 int sb_match_async(sb_ctx* ctx, sb_point* d_pts1, int n1, const float* d_feat1, const sb_point* d_pts2, int n2,
                    const float* d_feat2, void* stream);
 
+/* Consumer-side acceptance of match results (the reference draws every row's best candidate,
+ * main.cpp:59-70, and leaves the ratio test to the consumer of SurfPoint::ambiguity). Rows of set 1 with
+ * match >= 0 and ambiguity < max_ambiguity are compacted, in row order, into (idx1, idx2, score, ambiguity).
+ *   flags  SB_FILTER_LAPLACE: also require equal Laplacian signs (surf_structures.h:13)
+ *          SB_FILTER_CROSS:   also require d_pts2[idx2].match == idx1 (set 2 matched back with a second sb_match)
+ *   d_pairs  device array of `cap` pairs; h_pairs nullable host copy; *num_pairs the number kept (<= cap).       */
+typedef struct sb_pair { int idx1, idx2; float score, ambiguity; } sb_pair;
+#define SB_FILTER_LAPLACE 1
+#define SB_FILTER_CROSS 2
+int sb_match_filter(sb_ctx* ctx, const sb_point* d_pts1, int n1, const sb_point* d_pts2, int n2, float max_ambiguity,
+                    int flags, sb_pair* d_pairs, sb_pair* h_pairs, int cap, int* num_pairs);
+
 /* Batched, asynchronous form of detectAndCompute for independent frames (the frame loop of
  * main.cpp:239-245 without a host round trip per frame). nframes <= params.batch.
  *   d_images  frame f at d_images + f*image_stride (bytes), row pitch `pitch`
