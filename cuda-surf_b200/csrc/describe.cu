@@ -337,8 +337,9 @@ describe_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, 
 // advances: ~10 shared-memory updates per column instead of 8 per sample. The two half-warps take
 // even / odd lattice rows, 16 columns per pass, so 23..45-wide lattices keep 70-97 % of the lanes
 // busy. 12 integral loads per sample (the reference's two Haar boxes share four corners).
-struct __align__(16) RowEntry { float rpos, rfrac; int ri, rowoff; };
+struct __align__(16) RowEntry { float rpos, w1, w0; int rowoff; };  // w1 = bilinear weight of cell row ri+1, w0 = 1 - w1
 constexpr int kRowTab = 96;
+constexpr int kAhead = 1;  // rows (of one parity) the gathers run ahead of the arithmetic
 constexpr int kRowInvalid = -100;  // 'no current cell row' marker of the sweep
 
 template <int O>
@@ -358,7 +359,7 @@ __device__ __forceinline__ void emit_row(float* __restrict__ h, int lane, int W,
 }
 
 template <int O>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
 describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
                         long long desc_stride) {
@@ -390,6 +391,9 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
         // per-row table (same IEEE operations as the reference's per-sample arithmetic). Valid rows
         // (inside the descriptor window and the image) form one contiguous range [row_lo, row_hi).
         int row_lo = side, row_hi = 0;
+        // segcnt[s] = number of valid rows with ri <= s-1: the rows of cell row ri = s-1 are [row_lo + segcnt[s-1],
+        // row_lo + segcnt[s]) (ri only grows with the row), so the sweep flushes at segment ends, not per sample
+        int segcnt[5] = {0, 0, 0, 0, 0};
         for (int i0 = 0; i0 < side; i0 += 32) {
             const int ii = i0 + lane;
             const int i = ii - R;
@@ -400,7 +404,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
             const int ri = __float2int_rz(rx >= 0.f ? rx : __fsub_rn(rx, 1.f));
             if (ii < side) {
                 RowEntry t;
-                t.rpos = rpos; t.rfrac = __fsub_rn(rx, __int2float_rn(ri)); t.ri = ri; t.rowoff = r * ip;
+                t.rpos = rpos; t.w1 = __fsub_rn(rx, __int2float_rn(ri)); t.w0 = __fsub_rn(1.f, t.w1); t.rowoff = r * ip;
                 rowT[ii] = t;
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -408,6 +412,8 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                 row_lo = min(row_lo, i0 + __ffs(m) - 1);
                 row_hi = max(row_hi, i0 + 32 - __clz(m));
             }
+#pragma unroll
+            for (int sg = 0; sg < 5; sg++) segcnt[sg] += __popc(__ballot_sync(0xffffffffu, ok && ri <= sg - 1));
         }
         __syncwarp();
         const int sip = S * ip, sip1 = sip + ip;
@@ -428,15 +434,10 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                 const int* pB = I + c;
                 const int* pD = I + (c + S + 1);
                 asm volatile("" : "+l"(pA), "+l"(pB), "+l"(pD));
-                // Register accumulators for cell rows `cur` (lo) and `cur`+1 (hi): signed sum and sum of
-                // magnitudes of dx and dy; the reference's split by sign is (S -/+ A)/2 at flush time.
-                float sl[4], sh[4];
-#pragma unroll
-                for (int b = 0; b < 4; b++) { sl[b] = 0.f; sh[b] = 0.f; }
-                float xl[4], xh[4];  // SURF-128 only: the same sums restricted to samples with dy<0 / dx<0
-#pragma unroll
-                for (int b = 0; b < 4; b++) { xl[b] = 0.f; xh[b] = 0.f; }
-                int cur = kRowInvalid;
+                // Register accumulators for cell rows ri (lo) and ri+1 (hi): signed sum and sum of magnitudes of dx and dy;
+                // the reference's split by sign is (S -/+ A)/2 at flush time.
+                float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
+                float xlo[4] = {0.f, 0.f, 0.f, 0.f}, xhi[4] = {0.f, 0.f, 0.f, 0.f};  // SURF-128: the sums restricted to dy<0 / dx<0
                 auto flush = [&](int k, const float (&sv)[4], const float (&xv)[4]) {
                     float v[O];
                     if (O == 4) {
@@ -458,80 +459,79 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                 // r+S+1: 6 of the 12 values are carried in registers and an iteration gathers 8 (rows X and q),
                 //   haar_x = (qD + mB - mD - qB) - (qC + mA - mC - qA)
                 //   haar_y = (XD - XA) + (YD - YA) - (mD - mA) - (qD - qA)      (symmetric in z/u, so X/Y need no
-                // case split). Software-pipelined: the gathers of this lane's NEXT row are issued before the
-                // current row is consumed.
+                // case split).
+                // Software pipeline without register moves: three register sets (8 corners + the row's rpos, w0, w1)
+                // rotate through the roles previous / current / next, so the loop body is unrolled three times; the
+                // gathers of the NEXT row are issued before the current row is consumed.
                 const int e = 2 * step - S;
                 const bool carry = (e == 0 || e == 1);
                 const int offX = carry ? e * ip : 0, offY = carry ? ip - offX : ip;
-                auto gather8 = [&](int rowoff, int (&g)[8]) {
-                    const int ox = rowoff + offX, op = rowoff + sip1;
-                    g[0] = __ldg(pA + ox); g[1] = __ldg(pB + ox); g[2] = __ldg(pB + ox + 1); g[3] = __ldg(pD + ox);
-                    g[4] = __ldg(pA + op); g[5] = __ldg(pB + op); g[6] = __ldg(pB + op + 1); g[7] = __ldg(pD + op);
+                struct RowSet { int g[8]; float rpos, w0, w1; int rowoff; };
+                auto gather8 = [&](int ii, RowSet& r) {
+                    const RowEntry t = rowT[ii];
+                    r.rpos = t.rpos; r.w0 = t.w0; r.w1 = t.w1; r.rowoff = t.rowoff;
+                    const int ox = t.rowoff + offX, op = t.rowoff + sip1;
+                    r.g[0] = __ldg(pA + ox); r.g[1] = __ldg(pB + ox); r.g[2] = __ldg(pB + ox + 1); r.g[3] = __ldg(pD + ox);
+                    r.g[4] = __ldg(pA + op); r.g[5] = __ldg(pB + op); r.g[6] = __ldg(pB + op + 1); r.g[7] = __ldg(pD + op);
                 };
                 int ii = row_lo + half;
-                RowEntry t;
-                int g[8];
-                int m0 = 0, m1 = 0, m2 = 0, m3 = 0, yA = 0, yD = 0;
-                if (ii < row_hi) {
-                    t = rowT[ii];
-                    gather8(t.rowoff, g);
-                    const int om = t.rowoff - sip, oy = t.rowoff + offY;
-                    m0 = __ldg(pA + om); m1 = __ldg(pB + om); m2 = __ldg(pB + om + 1); m3 = __ldg(pD + om);
-                    yA = __ldg(pA + oy); yD = __ldg(pD + oy);
-                }
-                while (ii < row_hi) {
-                    const int in = ii + 2;
-                    RowEntry tn = t;
-                    int gn[8];
-                    if (in < row_hi) { tn = rowT[in]; gather8(tn.rowoff, gn); }
-                    if (t.ri != cur) {
-                        if (cur != kRowInvalid) {
-                            flush(cur, sl, xl);
-                            if (t.ri == cur + 1) {
+                int seg = 0, segend = row_lo + segcnt[0];
+                // one sample: prev = row two lattice steps up (its X row is this row's m, its q row this row's Y)
+                auto sample = [&](const RowSet& prev, const RowSet& cur, RowSet& next) {
+                    if (ii + 2 * kAhead < row_hi) gather8(ii + 2 * kAhead, next);
+                    while (ii >= segend) {  // the rows of cell row seg-1 are done: flush it, the upper half moves down
+                        if (seg >= 1) flush(seg - 1, lo, xlo);
 #pragma unroll
-                                for (int b = 0; b < 4; b++) { sl[b] = sh[b]; sh[b] = 0.f; xl[b] = xh[b]; xh[b] = 0.f; }
-                            } else {
-                                flush(cur + 1, sh, xh);
-#pragma unroll
-                                for (int b = 0; b < 4; b++) { sl[b] = 0.f; sh[b] = 0.f; xl[b] = 0.f; xh[b] = 0.f; }
-                            }
-                        }
-                        cur = t.ri;
+                        for (int b = 0; b < 4; b++) { lo[b] = hi[b]; hi[b] = 0.f; xlo[b] = xhi[b]; xhi[b] = 0.f; }
+                        seg++;
+                        // (selects, not an indexed array: segcnt stays in registers)
+                        const int cnt = seg == 1 ? segcnt[1] : seg == 2 ? segcnt[2] : seg == 3 ? segcnt[3] : segcnt[4];
+                        segend = seg <= W ? row_lo + cnt : (1 << 30);
                     }
+                    int m0 = prev.g[0], m1 = prev.g[1], m2 = prev.g[2], m3 = prev.g[3], yA = prev.g[4], yD = prev.g[7];
                     if (!carry) {
-                        // generic (S, step): rows z = r and u = r+1 are gathered as X and Y, m is re-read
-                        const int om = t.rowoff - sip, oy = t.rowoff + offY;
+                        // generic (S, step): rows z = r and u = r+1 were gathered as X and Y, m is re-read
+                        const int om = cur.rowoff - sip, oy = cur.rowoff + offY;
                         m0 = __ldg(pA + om); m1 = __ldg(pB + om); m2 = __ldg(pB + om + 1); m3 = __ldg(pD + om);
                         yA = __ldg(pA + oy); yD = __ldg(pD + oy);
                     }
-                    const float weight = s_lut2[__float2int_rz(__fmaf_rn(t.rpos, t.rpos, cpos2))];
-                    const int wx = (g[7] + m1 - m3 - g[5]) - (g[6] + m0 - m2 - g[4]);
-                    const int wy = (g[3] - g[0]) + (yD - yA) - (m3 - m0) - (g[7] - g[4]);
+                    const float weight = s_lut2[__float2int_rz(__fmaf_rn(cur.rpos, cur.rpos, cpos2))];
+                    const int wx = (cur.g[7] + m1 - m3 - cur.g[5]) - (cur.g[6] + m0 - m2 - cur.g[4]);
+                    const int wy = (cur.g[3] - cur.g[0]) + (yD - yA) - (m3 - m0) - (cur.g[7] - cur.g[4]);
                     const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(wx)), kR255);
                     const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(wy)), kR255);
-                    const float w1 = t.rfrac, w0 = __fsub_rn(1.f, w1);
-                    sl[0] = __fmaf_rn(a, w0, sl[0]); sl[1] = __fmaf_rn(fabsf(a), w0, sl[1]);
-                    sl[2] = __fmaf_rn(b, w0, sl[2]); sl[3] = __fmaf_rn(fabsf(b), w0, sl[3]);
-                    sh[0] = __fmaf_rn(a, w1, sh[0]); sh[1] = __fmaf_rn(fabsf(a), w1, sh[1]);
-                    sh[2] = __fmaf_rn(b, w1, sh[2]); sh[3] = __fmaf_rn(fabsf(b), w1, sh[3]);
+                    const float w0 = cur.w0, w1 = cur.w1;
+                    lo[0] = __fmaf_rn(a, w0, lo[0]); lo[1] = __fmaf_rn(fabsf(a), w0, lo[1]);
+                    lo[2] = __fmaf_rn(b, w0, lo[2]); lo[3] = __fmaf_rn(fabsf(b), w0, lo[3]);
+                    hi[0] = __fmaf_rn(a, w1, hi[0]); hi[1] = __fmaf_rn(fabsf(a), w1, hi[1]);
+                    hi[2] = __fmaf_rn(b, w1, hi[2]); hi[3] = __fmaf_rn(fabsf(b), w1, hi[3]);
                     if (O == 8) {
                         // the part of each sum with (dy<0) for the dx-sums, (dx<0) for the dy-sums
                         const float an = (b < 0.f) ? a : 0.f, bn = (a < 0.f) ? b : 0.f;
-                        xl[0] = __fmaf_rn(an, w0, xl[0]); xl[1] = __fmaf_rn(fabsf(an), w0, xl[1]);
-                        xl[2] = __fmaf_rn(bn, w0, xl[2]); xl[3] = __fmaf_rn(fabsf(bn), w0, xl[3]);
-                        xh[0] = __fmaf_rn(an, w1, xh[0]); xh[1] = __fmaf_rn(fabsf(an), w1, xh[1]);
-                        xh[2] = __fmaf_rn(bn, w1, xh[2]); xh[3] = __fmaf_rn(fabsf(bn), w1, xh[3]);
+                        xlo[0] = __fmaf_rn(an, w0, xlo[0]); xlo[1] = __fmaf_rn(fabsf(an), w0, xlo[1]);
+                        xlo[2] = __fmaf_rn(bn, w0, xlo[2]); xlo[3] = __fmaf_rn(fabsf(bn), w0, xlo[3]);
+                        xhi[0] = __fmaf_rn(an, w1, xhi[0]); xhi[1] = __fmaf_rn(fabsf(an), w1, xhi[1]);
+                        xhi[2] = __fmaf_rn(bn, w1, xhi[2]); xhi[3] = __fmaf_rn(fabsf(bn), w1, xhi[3]);
                     }
-                    // carry: this row's X becomes the next row's m, this row's q(A,D) its Y
-                    m0 = g[0]; m1 = g[1]; m2 = g[2]; m3 = g[3]; yA = g[4]; yD = g[7];
-                    t = tn;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) g[k] = gn[k];
-                    ii = in;
-                }
-                if (cur != kRowInvalid) {
-                    flush(cur, sl, xl);
-                    flush(cur + 1, sh, xh);
+                    ii += 2;
+                };
+                if (ii < row_hi) {
+                    RowSet r0, r1, r2;
+                    gather8(ii, r1);
+                    {   // prologue: the m row (r-S) and the Y row (r+1-e) of the first sample, in the layout of a previous set
+                        const int om = r1.rowoff - sip, oy = r1.rowoff + offY;
+                        r0.g[0] = __ldg(pA + om); r0.g[1] = __ldg(pB + om); r0.g[2] = __ldg(pB + om + 1); r0.g[3] = __ldg(pD + om);
+                        r0.g[4] = __ldg(pA + oy); r0.g[7] = __ldg(pD + oy); r0.g[5] = 0; r0.g[6] = 0;
+                        r0.rpos = 0.f; r0.w0 = 0.f; r0.w1 = 0.f; r0.rowoff = 0;
+                    }
+                    while (true) {
+                        sample(r0, r1, r2); if (ii >= row_hi) break;
+                        sample(r1, r2, r0); if (ii >= row_hi) break;
+                        sample(r2, r0, r1); if (ii >= row_hi) break;
+                    }
+                    // the last row's cell rows: ri = seg-1 (lo) and ri+1 (hi)
+                    if (seg >= 1) flush(seg - 1, lo, xlo);
+                    flush(seg, hi, xhi);
                 }
             }
         }
