@@ -30,7 +30,7 @@ struct sb_ctx {
     int device = 0, sm_count = 148;
     cudaStream_t stream = nullptr;
     // ingest / egress streams and per-chunk events of the pipelined host-buffer path (sb_detect_batch_host)
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, stream2 = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_done;
     // scratch, `batch` frame slots each
     int* d_integral = nullptr;
@@ -177,6 +177,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -387,11 +388,27 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
     // the egress stream -- so the H2D of chunk k+1, the kernels of chunk k and the D2H of chunk k-1
     // overlap (two copy engines, PCIe is full duplex). The reference does all of this serially per frame
     // with blocking copies (main.cpp:211-226, surf.cpp:302-303, 335-342).
-    const int chunk = nframes >= 32 ? 8 : (nframes >= 8 ? 4 : 1);
-    const int nchunks = (nframes + chunk - 1) / chunk;
+    // Chunk schedule: small chunks at both ends (the first upload and the last download are not hidden behind
+    // anything), full chunks in between, alternating over two compute streams so that the tail of one chunk's
+    // descriptor kernel overlaps the head of the next chunk.
+    int chunk = nframes >= 64 ? 16 : (nframes >= 32 ? 8 : (nframes >= 8 ? 4 : 1));
+    if (const char* e = getenv("SB_HOST_CHUNK")) chunk = std::max(1, atoi(e));  // tuning knob (experiments only)
+    std::vector<int> first;  // first frame of every chunk, plus nframes
+    {
+        std::vector<int> sizes, tail;
+        int left = nframes;
+        for (int r = 2; r < chunk && left > 2 * chunk; r *= 2) { sizes.push_back(r); tail.push_back(r); left -= 2 * r; }
+        while (left > 0) { const int c = std::min(chunk, left); sizes.push_back(c); left -= c; }
+        for (int i = (int)tail.size() - 1; i >= 0; i--) sizes.push_back(tail[i]);
+        int f = 0;
+        for (int c : sizes) { first.push_back(f); f += c; }
+        first.push_back(f);
+    }
+    const int nchunks = (int)first.size() - 1;
     if (!ctx->s_h2d) {
         CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     }
     while ((int)ctx->ev_in.size() < nchunks) {
         cudaEvent_t a = nullptr, b = nullptr;
@@ -400,10 +417,10 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
         CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
         ctx->ev_done.push_back(b);
     }
-    cudaStream_t st = ctx->stream;
     const size_t pstride = (size_t)P.max_pts, dstride_f = (size_t)P.max_pts * P.nfeatures;
     for (int k = 0; k < nchunks; k++) {
-        const int f0 = k * chunk, nf = std::min(chunk, nframes - f0);
+        const int f0 = first[k], nf = first[k + 1] - f0;
+        cudaStream_t st = (k & 1) ? ctx->stream2 : ctx->stream;
         if (dpitch == sw_) {
             CU(cudaMemcpyAsync(ctx->d_stage_img + f0 * dstride, h_images + f0 * fbytes, fbytes * nf, cudaMemcpyHostToDevice, ctx->s_h2d));
         } else {
@@ -421,7 +438,7 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
         CU(cudaEventRecord(ctx->ev_done[k], st));
     }
     for (int k = 0; k < nchunks; k++) {
-        const int f0 = k * chunk, nf = std::min(chunk, nframes - f0);
+        const int f0 = first[k], nf = first[k + 1] - f0;
         CU(cudaEventSynchronize(ctx->ev_done[k]));  // counts of chunk k are on the host; later chunks keep running
         CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[k], 0));
         for (int f = f0; f < f0 + nf; f++) {
@@ -435,7 +452,8 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
         }
     }
     CU(cudaStreamSynchronize(ctx->s_d2h));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream2));
     return SB_OK;
 }
 
