@@ -103,11 +103,11 @@ cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t imag
                             int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);
 cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, float* d_resp, cudaStream_t st);
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
-                       int* d_counts, cudaStream_t st);
+                       int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st);
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
                             cudaStream_t st);
-cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, cudaStream_t st);
+cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, cudaStream_t st);
 // grow-only device scratch of the matcher (split-bf16 operands, per-split group top-2), owned by the context
 struct MatchScratch {
     void* a = nullptr; void* b = nullptr; void* part = nullptr;

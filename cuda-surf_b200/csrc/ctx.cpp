@@ -37,6 +37,9 @@ struct sb_ctx {
     float* d_resp = nullptr;
     int *d_colsum = nullptr, *d_rowsum = nullptr, *d_tilesum = nullptr;
     int* d_counts = nullptr;
+    unsigned* d_cand = nullptr;   // NMS candidate queues, `batch` slots of cand_cap packed words
+    int* d_cand_count = nullptr;
+    int cand_cap = 0;
     uint8_t* d_up = nullptr;  // doubled=true: the 2x up-sampled frames, `batch` slots of up_pitch * P.h bytes
     int up_pitch = 0;
     // staging for the synchronous / host-buffer entry points
@@ -167,7 +170,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_integral); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
-    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_stage_img); cudaFree(ctx->d_stage_pts);
+    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_stage_img); cudaFree(ctx->d_stage_pts);
     cudaFree(ctx->d_stage_desc);
     free_match_scratch(ctx->match_ws);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -217,6 +220,11 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     ok(cudaMalloc((void**)&c->d_rowsum, rowsz));
     ok(cudaMalloc((void**)&c->d_tilesum, ttsz));
     ok(cudaMalloc((void**)&c->d_counts, sizeof(int) * B));
+    // candidates that survive the 3x3x3 test are ~1.1x the final keypoints; 4x max_pts never overflows in practice and
+    // an overflow only drops candidates (the reference's cap is racy as well)
+    c->cand_cap = (int)std::min<long long>(4LL * P.max_pts, 1LL << 24);
+    ok(cudaMalloc((void**)&c->d_cand, sizeof(unsigned) * (size_t)c->cand_cap * B));
+    ok(cudaMalloc((void**)&c->d_cand_count, sizeof(int) * B));
     if (P.doubled) {
         c->up_pitch = align_up(P.w, 128);
         ok(cudaMalloc((void**)&c->d_up, (size_t)c->up_pitch * P.h * B));
@@ -229,6 +237,7 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
         ok(cudaMemsetAsync(c->d_integral, 0, isz, c->stream));
         ok(cudaMemsetAsync(c->d_resp, 0, rsz, c->stream));
         ok(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * B, c->stream));
+        ok(cudaMemsetAsync(c->d_cand_count, 0, sizeof(int) * B, c->stream));
         ok(cudaStreamSynchronize(c->stream));
     }
     if (e != cudaSuccess) {
@@ -253,7 +262,7 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
         t += (long long)P.max_scale * P.oct[o].sw * P.oct[o].sh;
     }
     info->resp_floats = t;
-    info->kernels_per_frame = 2 /*integral*/ + 1 /*hessian*/ + 1 /*nms*/ + 1 /*clamp*/ + (P.upright ? 1 : 2);
+    info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + 2 /*hessian*/ + 2 /*nms*/ + 1 /*clamp*/ + (P.upright ? 1 : 2);
     return SB_OK;
 }
 
@@ -282,8 +291,9 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
     if (ev) CU(cudaEventRecord(ev[1], st));
     CU(launch_hessian(P, nframes, integral, resp, st));
     if (ev) CU(cudaEventRecord(ev[2], st));
-    CU(launch_nms(P, nframes, integral, resp, d_points, d_counts, st));
-    CU(launch_clamp_counts(d_counts, nframes, P.max_pts, st));
+    CU(launch_nms(P, nframes, integral, resp, d_points, d_counts, ctx->d_cand + (size_t)slot0 * ctx->cand_cap,
+                  ctx->d_cand_count + slot0, ctx->cand_cap, st));
+    CU(launch_clamp_counts(d_counts, nframes, P.max_pts, ctx->d_cand_count + slot0, st));
     if (ev) CU(cudaEventRecord(ev[3], st));
     if (d_desc)
         CU(launch_describe(P, nframes, integral, d_points, P.max_pts, d_counts, -1, d_desc,

@@ -101,10 +101,21 @@ __device__ __forceinline__ int laplace_sign(const int* __restrict__ I, int ip, i
     return (lxx + lyy > 0) ? 1 : -1;
 }
 
+// Two kernels. The scan touches every response value once and must run at memory speed, the refinement runs for
+// ~1.5 % of the cells and needs 60 registers; fused, the refinement's registers cut the scan's occupancy to a third
+// (ncu, fused version: 58 registers, 34 % warps active, 25 % of DRAM peak).
+//   nms_scan_kernel   thread per 2x2x2 cell: cell maximum, 0.8*thresh test, top-layer rule, 19-neighbour test;
+//                     survivors go to a per-frame candidate queue as one packed word (octave, layer, row, column)
+//   nms_refine_kernel thread per candidate: <= 5 quadratic fits, rejection tests, makePoint, append
+constexpr int kCandShiftS = 26, kCandShiftO = 29;  // packed candidate: c [0,13) | r [13,26) | s [26,29) | o [29,32)
+
 // grid (nms_tiles, nframes), block 32x8: one thread per 2x2(xy) x 2(scale) cell.
+// (A warp-cooperative neighbour test -- lane n loads neighbour n of one candidate, one ballot decides -- and four
+// cells per thread were tried: 2 % faster in a 64-frame batch, 40 % slower for a single frame, because a warp's
+// candidates then resolve one L2 round trip after the other. Not kept.)
 __global__ void __launch_bounds__(256)
-nms_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const float* __restrict__ Rbase,
-           sb_point* __restrict__ points, int* __restrict__ counts) {
+nms_scan_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase, unsigned* __restrict__ cand,
+                int* __restrict__ cand_count, int cand_cap) {
     const int f = blockIdx.y;
     const int tile = blockIdx.x;
     int o = 0;
@@ -125,27 +136,26 @@ nms_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const
     const int sw = q.sw, sh = q.sh, sp = q.sp, osz = q.osz;
     const float* src = Rbase + (size_t)f * P.rstride + q.resp_off;
 
-    bool keep = false;
-    float kx = 0.f, ky = 0.f, kscale = 0.f, kstrength = 0.f;
-    int klap = 1;
-
+    bool cand_ok = false;
+    unsigned packed = 0;
     if (k < ms - 1 && i < sh - mb && j < sw - mb) {
         const float* c0 = src + (size_t)k * osz + (size_t)i * sp + j;
         const float* c1 = c0 + osz;
-        // cell maximum in the reference's scan order, strict >
-        float best = __ldg(c0);
+        // cell maximum in the reference's scan order, strict > (surfd.cu:699-736)
+        const float v0 = __ldg(c0), v1 = __ldg(c0 + 1), v2 = __ldg(c0 + sp), v3 = __ldg(c0 + sp + 1);
+        const float v4 = __ldg(c1), v5 = __ldg(c1 + 1), v6 = __ldg(c1 + sp), v7 = __ldg(c1 + sp + 1);
+        float best = v0;
         int cas = 0;
-        float v;
-        v = __ldg(c0 + 1);      if (v > best) { best = v; cas = 1; }
-        v = __ldg(c0 + sp);     if (v > best) { best = v; cas = 2; }
-        v = __ldg(c0 + sp + 1); if (v > best) { best = v; cas = 3; }
-        v = __ldg(c1);          if (v > best) { best = v; cas = 4; }
-        v = __ldg(c1 + 1);      if (v > best) { best = v; cas = 5; }
-        v = __ldg(c1 + sp);     if (v > best) { best = v; cas = 6; }
-        v = __ldg(c1 + sp + 1); if (v > best) { best = v; cas = 7; }
-        bool cand = !(best < __fmul_rn(P.thresh, 0.8f)) && !(k + 1 == ms - 1 && cas > 3);
-        int s = k + (cas >> 2), r = i + ((cas >> 1) & 1), c = j + (cas & 1);
-        if (cand) {
+        if (v1 > best) { best = v1; cas = 1; }
+        if (v2 > best) { best = v2; cas = 2; }
+        if (v3 > best) { best = v3; cas = 3; }
+        if (v4 > best) { best = v4; cas = 4; }
+        if (v5 > best) { best = v5; cas = 5; }
+        if (v6 > best) { best = v6; cas = 6; }
+        if (v7 > best) { best = v7; cas = 7; }
+        bool cnd = !(best < __fmul_rn(P.thresh, 0.8f)) && !(k + 1 == ms - 1 && cas > 3);
+        const int s = k + (cas >> 2), r = i + ((cas >> 1) & 1), c = j + (cas & 1);
+        if (cnd) {
             // outward directions: the cell's other member along each axis sits at -d
             const int ds = (cas & 4) ? 1 : -1, dr = (cas & 2) ? 1 : -1, dc = (cas & 1) ? 1 : -1;
             const float* ctr = src + (size_t)s * osz + (size_t)r * sp + c;
@@ -155,20 +165,57 @@ nms_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const
             for (int a = -1; a <= 1; a++)
 #pragma unroll
                 for (int b = -1; b <= 1; b++)
-                    if (best < __ldg(L + a * sp + b)) cand = false;
+                    if (best < __ldg(L + a * sp + b)) cnd = false;
             // own layer s and inner layer s-ds: the five positions outside the cell's 2x2 footprint
 #pragma unroll
             for (int li = 0; li < 2; li++) {
                 const float* M = ctr - li * ds * osz;
                 const float* rowo = M + dr * sp;  // outward row: three
-                if (best < __ldg(rowo - 1)) cand = false;
-                if (best < __ldg(rowo)) cand = false;
-                if (best < __ldg(rowo + 1)) cand = false;
-                if (best < __ldg(M + dc)) cand = false;            // (r, c+dc)
-                if (best < __ldg(M - dr * sp + dc)) cand = false;  // (r-dr, c+dc)
+                if (best < __ldg(rowo - 1)) cnd = false;
+                if (best < __ldg(rowo)) cnd = false;
+                if (best < __ldg(rowo + 1)) cnd = false;
+                if (best < __ldg(M + dc)) cnd = false;            // (r, c+dc)
+                if (best < __ldg(M - dr * sp + dc)) cnd = false;  // (r-dr, c+dc)
             }
         }
-        if (cand) {
+        cand_ok = cnd;
+        packed = (unsigned)c | ((unsigned)r << 13) | ((unsigned)s << kCandShiftS) | ((unsigned)o << kCandShiftO);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, cand_ok);
+    if (m) {
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&cand_count[f], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (cand_ok) {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < cand_cap) cand[(size_t)f * cand_cap + slot] = packed;
+        }
+    }
+}
+
+// grid (ctas, nframes), 128 threads, grid-stride over the frame's candidates.
+__global__ void __launch_bounds__(128)
+nms_refine_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const float* __restrict__ Rbase,
+                  const unsigned* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
+                  sb_point* __restrict__ points, int* __restrict__ counts) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31;
+    const int ncand = min(cand_count[f], cand_cap);
+    const int ms = P.max_scale;
+    // whole warps iterate together (the append below is warp-aggregated)
+    for (int base_i = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base_i < ncand; base_i += gridDim.x * blockDim.x) {
+        const int ci = base_i + lane;
+        bool keep = false;
+        float kx = 0.f, ky = 0.f, kscale = 0.f, kstrength = 0.f;
+        int klap = 1, o = 0;
+        if (ci < ncand) {
+            const unsigned pk = cand[(size_t)f * cand_cap + ci];
+            o = (int)(pk >> kCandShiftO);
+            const int s = (int)((pk >> kCandShiftS) & 7u);
+            int r = (int)((pk >> 13) & 0x1fffu), c = (int)(pk & 0x1fffu);
+            const OctaveP& q = P.oct[o];
+            const int sw = q.sw, sh = q.sh, sp = q.sp, osz = q.osz;
+            const float* src = Rbase + (size_t)f * P.rstride + q.resp_off;
             float off[3] = {0.f, 0.f, 0.f};
             float strength = 0.f;
             int newr = r, newc = c;
@@ -206,42 +253,44 @@ nms_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const
                 keep = true;
             }
         }
-    }
-
-    // warp-aggregated append: one atomic per warp, hard bound on the slot
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-        const int leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&counts[f], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (keep) {
-            const int slot = base + __popc(m & ((1u << lane) - 1u));
-            if (slot < P.max_pts) {
-                // 48-byte SurfPoint as three 128-bit stores
-                float4* dst = reinterpret_cast<float4*>(points + (size_t)f * P.max_pts + slot);
-                dst[0] = make_float4(kx, ky, kscale, __int_as_float(o));
-                dst[1] = make_float4(kstrength, __int_as_float(klap), 0.f /*ori*/, 0.f /*score*/);
-                dst[2] = make_float4(__int_as_float(-1) /*match*/, 0.f, 0.f, 0.f);
+        // warp-aggregated append: one atomic per warp, hard bound on the slot
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&counts[f], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (keep) {
+                const int slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < P.max_pts) {
+                    // 48-byte SurfPoint as three 128-bit stores
+                    float4* dst = reinterpret_cast<float4*>(points + (size_t)f * P.max_pts + slot);
+                    dst[0] = make_float4(kx, ky, kscale, __int_as_float(o));
+                    dst[1] = make_float4(kstrength, __int_as_float(klap), 0.f /*ori*/, 0.f /*score*/);
+                    dst[2] = make_float4(__int_as_float(-1) /*match*/, 0.f, 0.f, 0.f);
+                }
             }
         }
     }
 }
 
-__global__ void clamp_counts_kernel(int* counts, int n, int max_pts) {
+// Clamp the keypoint counts to the capacity and re-arm the candidate counters for the next call (they are zero after
+// sb_create, and every pass leaves them zero again: no memset in the per-frame sequence).
+__global__ void clamp_counts_kernel(int* counts, int n, int max_pts, int* cand_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) counts[i] = min(counts[i], max_pts);
+    if (i < n) { counts[i] = min(counts[i], max_pts); cand_count[i] = 0; }
 }
 
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
-                       int* d_counts, cudaStream_t st) {
-    const dim3 grid(P.nms_tiles, nframes), block(32, 8);
-    nms_kernel<<<grid, block, 0, st>>>(P, d_integral, d_resp, d_points, d_counts);
+                       int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st) {
+    nms_scan_kernel<<<dim3(P.nms_tiles, nframes), dim3(32, 8), 0, st>>>(P, d_resp, d_cand, d_cand_count, cand_cap);
+    // ~5 k candidates per 1080p frame: 48 CTAs of 128 threads cover them in one pass, more are looped over
+    nms_refine_kernel<<<dim3(48, nframes), 128, 0, st>>>(P, d_integral, d_resp, d_cand, d_cand_count, cand_cap, d_points, d_counts);
     return cudaGetLastError();
 }
 
-cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, cudaStream_t st) {
-    clamp_counts_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(d_counts, nframes, max_pts);
+cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, cudaStream_t st) {
+    clamp_counts_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(d_counts, nframes, max_pts, d_cand_count);
     return cudaGetLastError();
 }
 
