@@ -607,11 +607,21 @@ void or_describe(const or_params* p, const int32_t* integral, int w, int h, cons
                 }
             }
         if (normalise) {
-            float sq[256];
+            /* surfd.cu:2460-2492. The reference's tree (halve down to 32, then +32,+16,...,+1) is only defined for
+             * nfeatures 64 and 128: for desc_wsz < 4 it reads shared memory past the nfeatures floats it allocated
+             * (:2474-2480 with 16 / 36 / 32 / 72 elements). There the intent -- the plain sum of squares -- is
+             * restated, in element order. */
+            float sq[256], total;
             for (int t = 0; t < NF; t++) sq[t] = d[t] * d[t];
-            for (int stride = NF / 2; stride > 0; stride >>= 1)
-                for (int t = 0; t < stride; t++) sq[t] += sq[t + stride];
-            const float f = 1.f / sqrtf(sq[0]);
+            if (NF == 64 || NF == 128) {
+                for (int stride = NF / 2; stride > 0; stride >>= 1)
+                    for (int t = 0; t < stride; t++) sq[t] += sq[t + stride];
+                total = sq[0];
+            } else {
+                total = 0.f;
+                for (int t = 0; t < NF; t++) total += sq[t];
+            }
+            const float f = 1.f / sqrtf(total);
             for (int t = 0; t < NF; t++) d[t] *= f;
         }
     }

@@ -477,3 +477,42 @@ def test_match_filter_ratio_laplace_cross():
         assert len(want) > 10
         assert np.array_equal(got["idx1"], want) and np.array_equal(got["idx2"], a["match"][want])
         assert np.array_equal(got["ambiguity"], a["ambiguity"][want]) and np.array_equal(got["score"], a["score"][want])
+
+
+# ---------------------------------------------------------------------------------------- non-default Surfor::init arguments
+
+@pytest.mark.parametrize("kw", [
+    dict(init_mask_size=6),                  # lobe 2 -> 4 layers per octave, even lobes
+    dict(init_mask_size=12),                 # lobe 4 -> 6 layers per octave
+    dict(sampling_step=1, noctaves=3),       # octave 0 sampled at every pixel
+    dict(sampling_step=3, noctaves=3),
+    dict(desc_wsz=2),                        # 2x2 cells, 16-d descriptors, 6x wider cell spacing
+    dict(desc_wsz=3, upright=False),         # 36-d, rotated
+    dict(noctaves=1),
+    dict(thresh=0.5, noctaves=2),            # many weak keypoints
+    dict(extend=True, desc_wsz=2),           # 32-d SURF-128 layout on a 2x2 grid
+])
+def test_init_argument_variants_vs_oracle(kw):
+    """Every Surfor::init argument (surf.h:27-29) away from the main.cpp defaults: maps bit-exact, keypoints and
+    descriptors as for the default configuration. These take the generic kernels (no octave-0 fast path, row tables
+    wider than 48 entries, other descriptor sizes)."""
+    sb = _sb()
+    w, h = 400, 300
+    a = dict(noctaves=4, thresh=4.0, init_mask_size=9, sampling_step=2, upright=True, extend=False, desc_wsz=4)
+    a.update(kw)
+    img = sb.synth_frame(w, h, 77)
+    det = sb.Surfor()
+    det.init(a["noctaves"], a["thresh"], False, a["init_mask_size"], a["sampling_step"], a["upright"], a["extend"], a["desc_wsz"],
+             w, h, max_pts=32768)
+    orc = ol.Oracle(a["noctaves"], a["thresh"], False, a["init_mask_size"], a["sampling_step"], a["upright"], a["extend"], a["desc_wsz"])
+    data, pts, desc = run_detect(det, img)
+    I = orc.integral(img)
+    assert np.array_equal(det.get_integral(), I)
+    assert np.array_equal(det.get_response().view(np.uint32), orc.hessian(I).view(np.uint32)), "Hessian maps differ"
+    opts, odesc = orc.detect_and_compute(img)
+    assert len(opts) > 10, len(opts)
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(opts, pts)
+    assert fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\n{describe_misses(miss_r, a['thresh'])}"
+    assert desc.shape[1] == odesc.shape[1] == a["desc_wsz"] ** 2 * (8 if a["extend"] else 4)
+    l2 = np.linalg.norm(desc[idx[ok]] - odesc[ok], axis=1)
+    assert (l2 <= (1e-3 if a["upright"] else 5e-3)).mean() >= 0.99, f"descriptor L2 max {l2.max():.3e}"
