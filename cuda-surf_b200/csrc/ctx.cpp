@@ -471,8 +471,6 @@ static int match_args_ok(sb_ctx* ctx, sb_point* d_pts1, int n1, const float* d_f
                          const float* d_feat2) {
     if (n1 < 0 || n2 < 0 || (n1 > 0 && (!d_pts1 || !d_feat1)) || (n2 > 0 && (!d_pts2 || !d_feat2)))
         return fail(ctx, SB_ERR_INVALID, "sb_match: bad argument");
-    if (ctx->P.nfeatures != 64 && ctx->P.nfeatures != 128)
-        return fail(ctx, SB_ERR_UNSUPPORTED, "sb_match: the tensor-core matcher is built for 64- and 128-d descriptors (desc_wsz 4)");
     return SB_OK;
 }
 

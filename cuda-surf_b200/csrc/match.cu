@@ -316,6 +316,62 @@ match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, c
     }
 }
 
+// ---------------------------------------------------------------------------- descriptor sizes other than 64 / 128
+//
+// desc_wsz < 4 gives 16-, 32-, 36- or 72-d descriptors (surf.cpp:78-79), which the 64-element K chunks of the tensor-core
+// path do not tile. Those sets are small problems (K <= 72); a warp per row of set 1 computes the reference's exact fp32
+// FFMA chain against every candidate: lane l takes p2 = l, l+32, ... -- group (p2 % 32) / 4 = l / 4 -- so a lane's own
+// running top-2 is a sub-sequence of its group's scan, four lanes merge into the group's (max, first arg max, second),
+// and the eight groups merge with the reference's rule (surfd.cu:2646-2664).
+__global__ void __launch_bounds__(128)
+match_generic_kernel(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, const sb_point* __restrict__ pts2, int ncand,
+                     const float* __restrict__ f2, int nf) {
+    extern __shared__ float s_row[];  // [4 warps][nf]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p1 = blockIdx.x * 4 + warp;
+    if (p1 >= n1) return;
+    float* a = s_row + warp * nf;
+    for (int d = lane; d < nf; d += 32) a[d] = f1[(size_t)p1 * nf + d];
+    __syncwarp();
+    float mx = 0.f, sc = 0.f;
+    int id = -1;
+    for (int p2 = lane; p2 < ncand; p2 += 32) {
+        const float* b = f2 + (size_t)p2 * nf;
+        float s = 0.f;
+        for (int d = 0; d < nf; d++) s = __fmaf_rn(a[d], __ldg(b + d), s);
+        if (s > mx) { sc = mx; mx = s; id = p2; }
+        else if (s > sc) sc = s;
+    }
+    // group = 4 consecutive lanes: the scan in increasing p2 keeps the first arg max and the second largest value
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o), osc = __shfl_xor_sync(0xffffffffu, sc, o);
+        const int oid = __shfl_xor_sync(0xffffffffu, id, o);
+        if (oid >= 0 && (omx > mx || (omx == mx && (id < 0 || oid < id)))) { sc = fmaxf(fmaxf(mx, sc), osc); mx = omx; id = oid; }
+        else sc = fmaxf(sc, fmaxf(oid >= 0 ? omx : 0.f, osc));
+    }
+    // merge (surfd.cu:2646-2664): start from group 0, the other groups contribute their maxima only
+    float m = __shfl_sync(0xffffffffu, mx, 0), s2 = __shfl_sync(0xffffffffu, sc, 0);
+    int idx = __shfl_sync(0xffffffffu, id, 0);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const float qm = __shfl_sync(0xffffffffu, mx, 4 * q);
+        const int qi = __shfl_sync(0xffffffffu, id, 4 * q);
+        if (idx != qi) {
+            if (qm > m) { s2 = fmaxf(m, s2); m = qm; idx = qi; }
+            else if (qm > s2) s2 = qm;
+        }
+    }
+    if (lane == 0) {
+        sb_point* p = pts1 + p1;
+        p->score = m;
+        p->match = idx;
+        p->match_x = idx >= 0 ? pts2[idx].x : 0.f;
+        p->match_y = idx >= 0 ? pts2[idx].y : 0.f;
+        p->ambiguity = __fdiv_rn(s2, __fadd_rn(m, 1e-6f));
+    }
+}
+
 // ---------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -390,7 +446,9 @@ cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_p
     if (n1 <= 0) return cudaSuccess;
     if (nfeatures == 64) return run_match<64>(d_pts1, n1, d_f1, d_pts2, n2, d_f2, ws, sm_count, st);
     if (nfeatures == 128) return run_match<128>(d_pts1, n1, d_f1, d_pts2, n2, d_f2, ws, sm_count, st);
-    return cudaErrorInvalidValue;  // desc_wsz < 4: no tensor-core tiling for K < 64 yet
+    if (nfeatures < 1 || nfeatures > 256) return cudaErrorInvalidValue;
+    match_generic_kernel<<<(n1 + 3) / 4, 128, 4 * nfeatures * sizeof(float), st>>>(d_pts1, n1, d_f1, d_pts2, n2 - (n2 & 31), d_f2, nfeatures);
+    return cudaGetLastError();
 }
 
 void free_match_scratch(MatchScratch& ws) {

@@ -516,3 +516,18 @@ def test_init_argument_variants_vs_oracle(kw):
     assert desc.shape[1] == odesc.shape[1] == a["desc_wsz"] ** 2 * (8 if a["extend"] else 4)
     l2 = np.linalg.norm(desc[idx[ok]] - odesc[ok], axis=1)
     assert (l2 <= (1e-3 if a["upright"] else 5e-3)).mean() >= 0.99, f"descriptor L2 max {l2.max():.3e}"
+    # matching for this descriptor size (16/32/36-d take the generic kernel, 64/128-d the tensor-core one)
+    torch = _torch()
+    d_img, whp = upload(img)
+    d1 = sb.initSurfData(32768, True, True)
+    f1 = det.detectAndCompute(d_img, d1, whp)
+    d_img2, _ = upload(sb.synth_frame(w, h, 77, 6, 2, 99))
+    d2 = sb.initSurfData(32768, True, True)
+    f2 = det.detectAndCompute(d_img2, d2, whp)
+    if d2.num_pts >= 32:
+        det.match(d1, d2, f1, f2)
+        got = d1.host_points()
+        want = ol.match(got, f1[: d1.num_pts].cpu().numpy(), d2.host_points(), f2[: d2.num_pts].cpu().numpy())
+        assert np.array_equal(got["match"], want["match"])
+        assert np.allclose(got["score"], want["score"], rtol=0, atol=1e-6)
+        assert np.allclose(got["ambiguity"], want["ambiguity"], rtol=0, atol=1e-5)
