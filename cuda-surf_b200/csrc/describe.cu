@@ -607,7 +607,8 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     const int need = (maxn + kWarpsPerCta - 1) / kWarpsPerCta;
     // blockIdx.x runs fastest, so ~2 CTAs per SM per frame keeps only a few frames' integral images
     // live at a time (L2-resident) while still covering the machine for a single frame
-    int ctas = sm_count * 2;
+    // (a single frame or a small batch fills the machine instead: 5 resident CTAs per SM)
+    int ctas = sm_count * (nframes >= 5 ? 2 : (nframes >= 3 ? 3 : 5));
     if (const char* e = getenv("SB_DESC_CTAS")) ctas = atoi(e);  // tuning knob (experiments only)
     if (ctas < 1) ctas = 1;
     if (ctas > need) ctas = need;
