@@ -16,6 +16,7 @@ constexpr int kMaxScale = 8;   // surfd.h:9
 constexpr int kMaxOctave = 8;  // surfd.h:10
 constexpr int kNBin = 72;      // surfd.h:11
 constexpr int kHwn = 6;        // surfd.h:14
+constexpr int kHessRows = 32;  // output rows per tile of the gather Hessian kernel (hessian.cu); 32 columns
 
 // One octave of the scale space (surf.cpp:240-294, surfd.cu:2844-2865, 3062-3073).
 struct OctaveP {

@@ -140,7 +140,7 @@ static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
             if (q.mb[q.nmb] < mbmin) mbmin = q.mb[q.nmb];
             q.nmb++;
         }
-        q.hess_tile0 = hess_tiles; q.hess_tx = (sw + 31) / 32; q.hess_ty = (sh + 7) / 8;
+        q.hess_tile0 = hess_tiles; q.hess_tx = (sw + 31) / 32; q.hess_ty = (sh + kHessRows - 1) / kHessRows;
         hess_tiles += q.hess_tx * q.hess_ty;
         const int cw = (sw - 2 * mbmin + 1) / 2, ch = (sh - 2 * mbmin + 1) / 2;  // 2x2 cells per row / column
         q.nms_tile0 = nms_tiles;

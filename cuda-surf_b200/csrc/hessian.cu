@@ -63,6 +63,10 @@ __device__ __forceinline__ float hessian_response(const int* __restrict__ I, int
     return __fmul_rn(det, norm);
 }
 
+// grid (tiles, nframes, layers), block 32x8. A CTA covers 32 x kHessRows outputs of one layer (a thread: kHessRows/8 rows,
+// 8 apart): with a 32x8 tile every CTA pulled its whole 70-pixel filter halo through L2 for 256 outputs (ncu: 94 MB of
+// L2->L1 traffic per frame for the 8.9 MB integral); the taller tile reuses the halo from L1. (Looping the layers inside
+// the CTA as well was 1 % faster in a 64-frame batch and 30 % slower for a single frame.)
 __global__ void __launch_bounds__(256)
 hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int first_tile) {
     const int f = blockIdx.y;
@@ -72,32 +76,33 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, f
     const OctaveP& q = P.oct[o];
     const int lt = tile - q.hess_tile0;
     const int ty = lt / q.hess_tx, tx = lt - ty * q.hess_tx;
-    const int ix = tx * 32 + threadIdx.x, iy = ty * 8 + threadIdx.y;
-    if (ix >= q.sw || iy >= q.sh) return;
-
+    const int ix = tx * 32 + threadIdx.x;
+    if (ix >= q.sw) return;
     const int* I = Ibase + (size_t)f * P.istride + P.ip;
     float* Rf = Rbase + (size_t)f * P.rstride;
-    const int cx = q.delta * ix, cy = q.delta * iy;
+    const int cx = q.delta * ix;
     const int ms = P.max_scale;
-    // blockIdx.z is the computed layer: the octaves this kernel handles are small and their gathers are L2-latency
-    // bound, so the layers run as separate CTAs instead of a serial loop per thread
-    const int i = blockIdx.z;
-    if (i >= q.nl) return;
-    {
+    const int i = blockIdx.z;  // the computed layer
+    if (i < q.nl) {
         const int b = q.b1[i];
-        if (ix < b || ix >= q.sw - b || iy < b || iy >= q.sh - b) return;
-        const float v = hessian_response(I, P.ip, cx, cy, q.l[i], q.norm[i]);
-        int s = q.s0 + i;
-        Rf[q.resp_off + (size_t)s * q.osz + (size_t)iy * q.sp + ix] = v;
-        // write-through of what halfImage would copy into the next octave(s)
-        int oo = o, x = ix, y = iy;
-        while (oo + 1 < P.noctaves && (s == ms - 3 || s == ms - 1) && (((x | y) & 1) == 0)) {
-            const OctaveP& n = P.oct[oo + 1];
-            x >>= 1; y >>= 1;
-            if (x >= n.sw || y >= n.sh) break;
-            s = (s == ms - 3) ? 0 : 1;
-            oo++;
-            Rf[n.resp_off + (size_t)s * n.osz + (size_t)y * n.sp + x] = v;
+        if (ix < b || ix >= q.sw - b) return;
+#pragma unroll 2
+        for (int u = 0; u < kHessRows / 8; u++) {
+            const int iy = ty * kHessRows + threadIdx.y + 8 * u;
+            if (iy < b || iy >= q.sh - b) continue;
+            const float v = hessian_response(I, P.ip, cx, q.delta * iy, q.l[i], q.norm[i]);
+            int s = q.s0 + i;
+            Rf[q.resp_off + (size_t)s * q.osz + (size_t)iy * q.sp + ix] = v;
+            // write-through of what halfImage would copy into the next octave(s)
+            int oo = o, x = ix, y = iy;
+            while (oo + 1 < P.noctaves && (s == ms - 3 || s == ms - 1) && (((x | y) & 1) == 0)) {
+                const OctaveP& n = P.oct[oo + 1];
+                x >>= 1; y >>= 1;
+                if (x >= n.sw || y >= n.sh) break;
+                s = (s == ms - 3) ? 0 : 1;
+                oo++;
+                Rf[n.resp_off + (size_t)s * n.osz + (size_t)y * n.sp + x] = v;
+            }
         }
     }
 }
@@ -126,8 +131,10 @@ __host__ __device__ constexpr int corner_off(int dx, int dy) {
     return (((dy + kHalo) & 1) * 2 + ((dx + kHalo) & 1)) * kPlane + ((dy + kHalo) >> 1) * kQW + ((dx + kHalo) >> 1);
 }
 
+// ctr = the four corners (0,0), (1,0), (0,1), (1,1) [as (dx,dy)] around the sample: every layer's Dxy uses them, so
+// they are read once per sample instead of once per layer (16 of the 160 shared-memory words of a sample)
 template <int L>
-__device__ __forceinline__ float response_smem(const int* __restrict__ b, float norm) {
+__device__ __forceinline__ float response_smem(const int* __restrict__ b, float norm, const int (&ctr)[4]) {
     constexpr int x2 = L / 2, x3 = 2 * x2, x4 = 3 * x2;
 #define C_(dx, dy) b[corner_off(dx, dy)]
     // same corners as hessian_response(): rows/cols are those of getSum (surfd.cu:334-343)
@@ -137,10 +144,10 @@ __device__ __forceinline__ float response_smem(const int* __restrict__ b, float 
     const int tall = C_(x3 + 1, L + x2 + 1) + C_(-x3, -L - x2) - C_(x3 + 1, -L - x2) - C_(-x3, L + x2 + 1);
     const int midy = C_(x3 + 1, x2 + 1) + C_(-x3, -x2) - C_(x3 + 1, -x2) - C_(-x3, x2 + 1);
     const int dyy = tall - 3 * midy;
-    const int tr = C_(x4 + 1, 1) + C_(0, -x4) - C_(x4 + 1, -x4) - C_(0, 1);
-    const int bl = C_(1, x4 + 1) + C_(-x4, 0) - C_(1, 0) - C_(-x4, x4 + 1);
-    const int br = C_(x4 + 1, x4 + 1) + C_(0, 0) - C_(x4 + 1, 0) - C_(0, x4 + 1);
-    const int tl = C_(1, 1) + C_(-x4, -x4) - C_(1, -x4) - C_(-x4, 1);
+    const int tr = C_(x4 + 1, 1) + C_(0, -x4) - C_(x4 + 1, -x4) - ctr[2];
+    const int bl = C_(1, x4 + 1) + C_(-x4, 0) - ctr[1] - C_(-x4, x4 + 1);
+    const int br = C_(x4 + 1, x4 + 1) + ctr[0] - C_(x4 + 1, 0) - C_(0, x4 + 1);
+    const int tl = ctr[3] + C_(-x4, -x4) - C_(1, -x4) - C_(-x4, 1);
     const int dxy = tr + bl - br - tl;
 #undef C_
     const float fxy = __fmul_rn(0.6f, __int2float_rn(dxy));
@@ -153,11 +160,12 @@ __device__ __forceinline__ float response_smem(const int* __restrict__ b, float 
 }
 
 template <int L, int LAYER>
-__device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict__ b, float* __restrict__ Rf, int ix, int iy) {
+__device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict__ b, float* __restrict__ Rf, int ix, int iy,
+                                           const int (&ctr)[4]) {
     const OctaveP& q = P.oct[0];
     const int bd = q.b1[LAYER];
     if (ix < bd || ix >= q.sw - bd || iy < bd || iy >= q.sh - bd) return;
-    const float v = response_smem<L>(b, q.norm[LAYER]);
+    const float v = response_smem<L>(b, q.norm[LAYER], ctr);
     Rf[q.resp_off + (size_t)LAYER * q.osz + (size_t)iy * q.sp + ix] = v;
     // layers 2 and 4 are what halfImage copies into layers 0 and 1 of octave 1 (surf.cpp:250-258)
     if ((LAYER == 2 || LAYER == 4) && P.noctaves > 1 && ((ix | iy) & 1) == 0) {
@@ -194,11 +202,12 @@ hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
         const int lyy = ly + 8 * hrow;
         const int iy = kTH * ty + lyy;
         const int* b = patch + lyy * kQW + lx;
-        layer_smem<3, 0>(P, b, Rf, ix, iy);
-        layer_smem<5, 1>(P, b, Rf, ix, iy);
-        layer_smem<7, 2>(P, b, Rf, ix, iy);
-        layer_smem<9, 3>(P, b, Rf, ix, iy);
-        layer_smem<11, 4>(P, b, Rf, ix, iy);
+        const int ctr[4] = {b[corner_off(0, 0)], b[corner_off(1, 0)], b[corner_off(0, 1)], b[corner_off(1, 1)]};
+        layer_smem<3, 0>(P, b, Rf, ix, iy, ctr);
+        layer_smem<5, 1>(P, b, Rf, ix, iy, ctr);
+        layer_smem<7, 2>(P, b, Rf, ix, iy, ctr);
+        layer_smem<9, 3>(P, b, Rf, ix, iy, ctr);
+        layer_smem<11, 4>(P, b, Rf, ix, iy, ctr);
     }
 }
 
