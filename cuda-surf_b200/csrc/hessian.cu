@@ -17,43 +17,9 @@
 
 namespace sb {
 
-// det = r^2 (Dxx*Dyy - (0.6*Dxy)^2) * norm with the exact operation order of the reference's
-// sm_100a SASS (surfd.cu:353-366): t=(float(Dxy)*0.6f)^2; det=fma(Dxx,Dyy,-t); det*=r*r; det*=norm
-__device__ __forceinline__ float hessian_response(const int* __restrict__ I, int ip, int cx, int cy, int l, float norm) {
-    const int x2 = l >> 1, x3 = x2 + x2, x4 = x2 + x3;
-    // Dxx: (2l+2*x2+1) x (2*x3+1) box minus 3x its central (2*x2+1)-wide part; rows shared
-    int dxx, dyy, dxy;
-    {
-        const int* r0 = I + (cy - x3) * ip;
-        const int* r1 = I + (cy + x3 + 1) * ip;
-        const int a0 = cx - l - x2, a1 = cx - x2, a2 = cx + x2 + 1, a3 = cx + l + x2 + 1;
-        const int wide = __ldg(r1 + a3) + __ldg(r0 + a0) - __ldg(r0 + a3) - __ldg(r1 + a0);
-        const int mid = __ldg(r1 + a2) + __ldg(r0 + a1) - __ldg(r0 + a2) - __ldg(r1 + a1);
-        dxx = wide - 3 * mid;
-    }
-    {
-        const int c0 = cx - x3, c1 = cx + x3 + 1;
-        const int* r0 = I + (cy - l - x2) * ip;
-        const int* r1 = I + (cy - x2) * ip;
-        const int* r2 = I + (cy + x2 + 1) * ip;
-        const int* r3 = I + (cy + l + x2 + 1) * ip;
-        const int tall = __ldg(r3 + c1) + __ldg(r0 + c0) - __ldg(r0 + c1) - __ldg(r3 + c0);
-        const int mid = __ldg(r2 + c1) + __ldg(r1 + c0) - __ldg(r1 + c1) - __ldg(r2 + c0);
-        dyy = tall - 3 * mid;
-    }
-    {
-        // four (x4+1)^2 quadrant boxes sharing the centre pixel row/column
-        const int* ra = I + (cy - x4) * ip;
-        const int* rb = I + cy * ip;
-        const int* rc = I + (cy + 1) * ip;
-        const int* rd = I + (cy + x4 + 1) * ip;
-        const int A = cx - x4, B = cx, C = cx + 1, D = cx + x4 + 1;
-        const int tr = __ldg(rc + D) + __ldg(ra + B) - __ldg(ra + D) - __ldg(rc + B);
-        const int bl = __ldg(rd + C) + __ldg(rb + A) - __ldg(rb + C) - __ldg(rd + A);
-        const int br = __ldg(rd + D) + __ldg(rb + B) - __ldg(rb + D) - __ldg(rd + B);
-        const int tl = __ldg(rc + C) + __ldg(ra + A) - __ldg(ra + C) - __ldg(rc + A);
-        dxy = tr + bl - br - tl;
-    }
+// det = r^2 (Dxx*Dyy - (0.6*Dxy)^2) * norm with the exact operation order of the reference's sm_100a SASS
+// (surfd.cu:353-366): t=(float(Dxy)*0.6f)^2; det=fma(Dxx,Dyy,-t); det*=r*r; det*=norm
+__device__ __forceinline__ float hessian_det(int dxx, int dyy, int dxy, float norm) {
     const float fxy = __fmul_rn(0.6f, __int2float_rn(dxy));
     const float t = __fmul_rn(fxy, fxy);
     float det = __fmaf_rn(__int2float_rn(dxx), __int2float_rn(dyy), -t);
@@ -61,6 +27,42 @@ __device__ __forceinline__ float hessian_response(const int* __restrict__ I, int
     constexpr float rr = r255 * r255;  // float product, folded at compile time like the reference's r*r
     det = __fmul_rn(det, rr);
     return __fmul_rn(det, norm);
+}
+
+// The 32 box corners of a sample lie on 10 rows and 10 columns (same corners as getSum, surfd.cu:334-343):
+//   rows    Dxx: -x3, x3+1 | Dyy: -l-x2, -x2, x2+1, l+x2+1 | Dxy: -x4, 0, 1, x4+1
+//   columns Dxx: -l-x2, -x2, x2+1, l+x2+1 | Dyy: -x3, x3+1 | Dxy: -x4, 0, 1, x4+1
+// ROW(dy) gives a 64-bit row pointer, COL(dx) a 32-bit element offset; the pointers are made opaque so that every
+// gather is ONE IMAD.WIDE (offset * 4 + pointer) + LDG -- written naively the compiler spent 7 integer instructions
+// of 64-bit address arithmetic per load (ncu: 340 instructions per sample, 74 % issue utilisation).
+template <class RowF, class ColF>
+__device__ __forceinline__ float hessian_corners(RowF ROW, ColF COL, int l, float norm) {
+    const int x2 = l >> 1, x3 = x2 + x2, x4 = x2 + x3;
+    const int* r[10] = {ROW(-x3), ROW(x3 + 1), ROW(-l - x2), ROW(-x2), ROW(x2 + 1), ROW(l + x2 + 1), ROW(-x4), ROW(0), ROW(1), ROW(x4 + 1)};
+    const int c[10] = {COL(-l - x2), COL(-x2), COL(x2 + 1), COL(l + x2 + 1), COL(-x3), COL(x3 + 1), COL(-x4), COL(0), COL(1), COL(x4 + 1)};
+#pragma unroll
+    for (int k = 0; k < 10; k++) asm volatile("" : "+l"(r[k]));
+#define G_(ri, ci) __ldg(r[ri] + c[ci])
+    const int wide = G_(1, 3) + G_(0, 0) - G_(0, 3) - G_(1, 0);
+    const int midx = G_(1, 2) + G_(0, 1) - G_(0, 2) - G_(1, 1);
+    const int dxx = wide - 3 * midx;
+    const int tall = G_(5, 5) + G_(2, 4) - G_(2, 5) - G_(5, 4);
+    const int midy = G_(4, 5) + G_(3, 4) - G_(3, 5) - G_(4, 4);
+    const int dyy = tall - 3 * midy;
+    // four (x4+1)^2 quadrant boxes sharing the centre pixel row/column: rows a=6, b=7, c=8, d=9; columns A=6, B=7, C=8, D=9
+    const int tr = G_(8, 9) + G_(6, 7) - G_(6, 9) - G_(8, 7);
+    const int bl = G_(9, 8) + G_(7, 6) - G_(7, 8) - G_(9, 6);
+    const int br = G_(9, 9) + G_(7, 7) - G_(7, 9) - G_(9, 7);
+    const int tl = G_(8, 8) + G_(6, 6) - G_(6, 8) - G_(8, 6);
+    const int dxy = tr + bl - br - tl;
+#undef G_
+    return hessian_det(dxx, dyy, dxy, norm);
+}
+
+// row-major padded integral I (pitch ip)
+__device__ __forceinline__ float hessian_response(const int* __restrict__ I, int ip, int cx, int cy, int l, float norm) {
+    const int* base = I + (size_t)cy * ip + cx;
+    return hessian_corners([&](int dy) { return base + dy * ip; }, [&](int dx) { return dx; }, l, norm);
 }
 
 // grid (tiles, nframes, layers), block 32x8. A CTA covers 32 x kHessRows outputs of one layer (a thread: kHessRows/8 rows,
