@@ -109,10 +109,33 @@ def algorithmic_bytes(info, noct, n_kp, nfeat):
             "describe": b_int + b_kp + b_desc}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off: with 8 ranks the host
+    legs of `e2e` otherwise cross the socket interconnect. Best effort; returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, world, local_rank, dist):
     import torch
     import cuda_surf_b200 as sb
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     B = args.batch
     det = sb.Surfor()
@@ -242,7 +265,8 @@ def run_ours(args, rank, world, local_rank, dist):
                                        f"batch of {B} distinct frames per GPU per step (configs[3] sharding)",
                            "frames_per_step_per_gpu": B, "keypoints_per_frame": kp_mean,
                            "l2_policy": f"inputs+intermediates per step {B * (W * H + 23.6e6) / 1e6:.0f} MB > 126 MB L2",
-                           "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+                           "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                           "host_numa_binding": numa},
                 "e2e": e2e, "gpu_launches": kpf * args.steps, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "latency": lat, "impl": "ours"}
         print(json.dumps(line))

@@ -65,14 +65,18 @@ __device__ __forceinline__ float hessian_response(const int* __restrict__ I, int
     return hessian_corners([&](int dy) { return base + dy * ip; }, [&](int dx) { return dx; }, l, norm);
 }
 
-// grid (tiles, nframes, layers), block 32x8. A CTA covers 32 x kHessRows outputs of one layer (a thread: kHessRows/8 rows,
+// grid (tiles * layers, nframes), block 32x8; the layer is the fastest-varying part of blockIdx.x, so the layers of a
+// tile -- and all tiles of a frame -- run while that frame's integral is in L2 (with the layer as blockIdx.z every layer
+// swept all 64 frames again: ncu, 25 MB of DRAM reads per frame for the 8.9 MB integral). A CTA covers 32 x kHessRows outputs of one layer (a thread: kHessRows/8 rows,
 // 8 apart): with a 32x8 tile every CTA pulled its whole 70-pixel filter halo through L2 for 256 outputs (ncu: 94 MB of
 // L2->L1 traffic per frame for the 8.9 MB integral); the taller tile reuses the halo from L1. (Looping the layers inside
 // the CTA as well was 1 % faster in a 64-frame batch and 30 % slower for a single frame.)
 __global__ void __launch_bounds__(256)
-hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int first_tile) {
+hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int first_tile,
+               int nlayers) {
     const int f = blockIdx.y;
-    const int tile = blockIdx.x + first_tile;
+    const int tile = blockIdx.x / nlayers + first_tile;
+    const int i = blockIdx.x - (blockIdx.x / nlayers) * nlayers;  // the computed layer
     int o = 0;
     while (o + 1 < P.noctaves && tile >= P.oct[o + 1].hess_tile0) o++;
     const OctaveP& q = P.oct[o];
@@ -84,7 +88,6 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, f
     float* Rf = Rbase + (size_t)f * P.rstride;
     const int cx = q.delta * ix;
     const int ms = P.max_scale;
-    const int i = blockIdx.z;  // the computed layer
     if (i < q.nl) {
         const int b = q.b1[i];
         if (ix < b || ix >= q.sw - b) return;
@@ -227,8 +230,8 @@ cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, f
         for (int o = 0; o < P.noctaves; o++)
             if (P.oct[o].hess_tile0 >= first_tile && P.oct[o].nl > maxnl) maxnl = P.oct[o].nl;
         // (grid.y is the frame: the integral / response slots are indexed by blockIdx.y in every kernel)
-        const dim3 grid(P.hess_tiles - first_tile, nframes, maxnl), block(32, 8);
-        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral, d_resp, first_tile);
+        const dim3 grid((P.hess_tiles - first_tile) * maxnl, nframes), block(32, 8);
+        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral, d_resp, first_tile, maxnl);
     }
     return cudaGetLastError();
 }
