@@ -193,8 +193,18 @@ def run_ours(args, rank, world, local_rank, dist):
     ach = ab[names[top]] * B / (stage[top] / 1e3) / 1e9
     per_stage = {n: {"ms": float(stage[i]), "gbs": ab[n] * B / (stage[i] / 1e3) / 1e9,
                      "frac": ab[n] * B / (stage[i] / 1e3) / 1e9 / peak} for i, n in enumerate(names)}
+    # DRAM bytes of the dominant kernel per launch, from the committed ncu capture of the same batch size
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        kmap = {"describe": "describe_upright_kernel<4>", "nms": "nms_scan_kernel", "hessian": "hessian_o0_kernel"}
+        if tj.get("batch") == B and names[top] in kmap:
+            traffic = tj["kernels"][kmap[names[top]]]["traffic_bytes"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": names[top], "achieved": ach, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "stages": per_stage,
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "algorithmic_bytes_per_launch": ab[names[top]] * B, "stages": per_stage,
                 "pipeline_frac": sum(ab.values()) * B / (float(stage.sum()) / 1e3) / 1e9 / peak}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory both ways)

@@ -244,7 +244,7 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ a, const fl
     float s = 0.f;
     const float4* a4 = reinterpret_cast<const float4*>(a);
     const float4* b4 = reinterpret_cast<const float4*>(b);
-#pragma unroll 4
+#pragma unroll 8
     for (int d = 0; d < NF / 4; d++) {
         const float4 x = __ldg(a4 + d), y = __ldg(b4 + d);
         s = __fmaf_rn(x.x, y.x, s); s = __fmaf_rn(x.y, y.y, s); s = __fmaf_rn(x.z, y.z, s); s = __fmaf_rn(x.w, y.w, s);
@@ -267,15 +267,23 @@ match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, c
     // tensor-core top-2 of the group across the splits (ties: lower index, as a running scan would keep)
     float v1 = 0.f, v2 = 0.f;
     int i1 = -1, i2 = -1;
-    for (int s = 0; s < nsplit; s++) {
-        const Top2 c = part[((size_t)s * n1pad + p1) * 8 + g];  // 128 contiguous bytes per (split,row) across the warp
-        const float cv[2] = {c.mx, c.sc};
-        const int ci[2] = {c.imx, c.isc};
+    // (loads of eight splits are issued together: one L2 round trip per eight, not per split)
+    for (int s0 = 0; s0 < nsplit; s0 += 8) {
+        Top2 cs[8];
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
-            if (ci[q] < 0) continue;
-            if (cv[q] > v1 || (cv[q] == v1 && i1 >= 0 && ci[q] < i1)) { v2 = v1; i2 = i1; v1 = cv[q]; i1 = ci[q]; }
-            else if (cv[q] > v2 || (cv[q] == v2 && i2 >= 0 && ci[q] < i2)) { v2 = cv[q]; i2 = ci[q]; }
+        for (int u = 0; u < 8; u++)
+            cs[u] = s0 + u < nsplit ? part[((size_t)(s0 + u) * n1pad + p1) * 8 + g]  // 128 contiguous bytes per (split,row) across the warp
+                                    : Top2{0.f, 0.f, -1, -1};
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const float cv[2] = {cs[u].mx, cs[u].sc};
+            const int ci[2] = {cs[u].imx, cs[u].isc};
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                if (ci[q] < 0) continue;
+                if (cv[q] > v1 || (cv[q] == v1 && i1 >= 0 && ci[q] < i1)) { v2 = v1; i2 = i1; v1 = cv[q]; i1 = ci[q]; }
+                else if (cv[q] > v2 || (cv[q] == v2 && i2 >= 0 && ci[q] < i2)) { v2 = cv[q]; i2 = ci[q]; }
+            }
         }
     }
     // candidate of this lane: the pair in increasing index order (k = 0 first)
