@@ -36,13 +36,17 @@ namespace {
 constexpr int kBM = 128;        // rows of F1 per CTA == TMEM lanes
 constexpr int kSwizzleRow = 128;  // bytes per operand row chunk (64 bf16) == one 128B-swizzle row
 
+constexpr int kStages = 2;      // B' tiles in flight == TMEM accumulators
+constexpr int kEpiWarps = 8;    // epilogue warps; warp kEpiWarps is the producer (TMA + MMA issue)
+
 template <int NF> struct MatchCfg {
     static constexpr int KCH = 3 * NF / 64;            // 64-element K chunks of the split operands
     static constexpr int KTOT = 3 * NF;                // K of the tensor-core GEMM
-    static constexpr int BN = NF == 64 ? 256 : 128;    // columns (descriptors of set 2) per tile
+    static constexpr int BN = NF == 64 ? 128 : 64;     // columns (descriptors of set 2) per tile: two stages must fit
     static constexpr int A_BYTES = KCH * kBM * kSwizzleRow;
     static constexpr int B_BYTES = KCH * BN * kSwizzleRow;
-    static constexpr int SMEM = A_BYTES + B_BYTES + 1024 /*alignment slack*/ + 64 /*barriers*/;
+    static constexpr int SMEM = A_BYTES + kStages * B_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+    static constexpr int TMEM_COLS = kStages * BN;     // 256 / 128: a power of two >= 32
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,10 +145,15 @@ __global__ void match_prep(const float* __restrict__ fa, int na, int na_pad, __n
 }
 
 // ---------------------------------------------------------------------------- 2. tensor-core scores + fused group top-2
-struct Top2 { float mx, sc; int imx, isc; };  // 16 bytes
+struct __align__(16) Top2 { float mx, sc; int imx, isc; };  // 16 bytes, moved as one 128-bit word
 
+// Warp-specialised and double-buffered: warp 8 (one thread) runs the operand pipeline -- TMA of tile i+1 into the
+// other shared-memory stage, tcgen05.mma of tile i into the other TMEM accumulator -- while warps 0-7 run the top-2
+// epilogue of tile i-1 out of TMEM. Per stage three mbarriers: `full` (TMA landed), `mma` (tcgen05.commit: accumulator
+// ready, operands consumed), `free` (the eight epilogue warps have read the accumulator). Round-1 v1 did load -> MMA ->
+// epilogue strictly one after the other (ncu: tensor pipe active 12.5 % of the kernel).
 template <int NF>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__((kEpiWarps + 1) * 32, 1)
 match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles, int tiles_per_split,
           int n1pad, Top2* __restrict__ part) {
     using Cfg = MatchCfg<NF>;
@@ -152,24 +161,24 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                    // KCH chunks of 128 rows x 128 B
-    uint8_t* sB = smem + Cfg::A_BYTES;     // KCH chunks of BN rows x 128 B
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + Cfg::B_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-    const uint32_t bar_load = smem_u32(&bars[0]), bar_mma = smem_u32(&bars[1]);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int quarter = warp & 3;    // TMEM lane quarter this warp may read (warp id % 4)
-    const int chalf = warp >> 2;     // which half of the tile's columns this warp scans
+    uint8_t* sB = smem + Cfg::A_BYTES;     // kStages x (KCH chunks of BN rows x 128 B)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + kStages * Cfg::B_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rb = blockIdx.x, split = blockIdx.y;
     const int t0 = split * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
+    const int n = t1 - t0;
+    auto bar_full = [&](int st) { return smem_u32(&bars[st]); };
+    auto bar_mma = [&](int st) { return smem_u32(&bars[kStages + st]); };
+    auto bar_free = [&](int st) { return smem_u32(&bars[2 * kStages + st]); };
 
     if (tid == 0) {
-        mbar_init(bar_load, 1);
-        mbar_init(bar_mma, 1);
+        for (int st = 0; st < kStages; st++) { mbar_init(bar_full(st), 1); mbar_init(bar_mma(st), 1); mbar_init(bar_free(st), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: BN fp32 accumulator columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    if (warp == 1) {  // TMEM: kStages accumulators of BN fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -177,65 +186,86 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    float mx[8], sc[8];
-    int imx[8], isc[8];
+    if (warp == kEpiWarps) {
+        // ------------------------------------------------------------------ producer: one thread
+        if (lane == 0 && n > 0) {
+            constexpr uint32_t idesc = umma_idesc(kBM, BN);
+            auto issue_tma = [&](int i) {  // tile t0+i into stage i % kStages (and, once, the CTA's rows of A')
+                const int st = i % kStages;
+                mbar_expect_tx(bar_full(st), Cfg::B_BYTES + (i == 0 ? Cfg::A_BYTES : 0));
+                if (i == 0)
+                    for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sA + c * kBM * kSwizzleRow), &mapA, bar_full(st), c * 64, rb * kBM);
+                for (int c = 0; c < KCH; c++)
+                    tma_load_2d(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow), &mapB, bar_full(st), c * 64, (t0 + i) * BN);
+            };
+            issue_tma(0);
+            for (int i = 0; i < n; i++) {
+                const int st = i % kStages, use = i / kStages;
+                if (i + 1 < n) {
+                    // stage (i+1) % kStages was last read by the MMAs of tile i+1-kStages
+                    if (i + 1 >= kStages) mbar_wait(bar_mma((i + 1) % kStages), ((i + 1) / kStages - 1) & 1);
+                    issue_tma(i + 1);
+                }
+                mbar_wait(bar_full(st), use & 1);
+                if (use >= 1) mbar_wait(bar_free(st), (use - 1) & 1);  // the epilogue of tile i-kStages has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // D[128 x BN] = sum over K chunks and 16-element K steps
+                for (int c = 0; c < KCH; c++) {
+                    const uint64_t da = umma_desc(smem_u32(sA + c * kBM * kSwizzleRow));
+                    const uint64_t db = umma_desc(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow));
 #pragma unroll
-    for (int g = 0; g < 8; g++) { mx[g] = 0.f; sc[g] = 0.f; imx[g] = -1; isc[g] = -1; }
-
-    uint32_t ph_load = 0, ph_mma = 0;
-    constexpr uint32_t idesc = umma_idesc(kBM, BN);
-    for (int t = t0; t < t1; t++) {
-        if (tid == 0) {
-            // operands: this tile of B' (and, once, the CTA's rows of A') by TMA into swizzled smem
-            const uint32_t bytes = Cfg::B_BYTES + (t == t0 ? Cfg::A_BYTES : 0);
-            mbar_expect_tx(bar_load, bytes);
-            if (t == t0)
-                for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sA + c * kBM * kSwizzleRow), &mapA, bar_load, c * 64, rb * kBM);
-            for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sB + c * BN * kSwizzleRow), &mapB, bar_load, c * 64, t * BN);
-            mbar_wait(bar_load, ph_load);
+                    for (int k = 0; k < 4; k++)  // +32 bytes (2 x 16 B units) per K step inside the swizzle row
+                        umma_bf16(tmem_d + st * BN, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
+                }
+                umma_commit(bar_mma(st));  // arrives when the MMAs above have completed (implies before_thread_sync)
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue: 8 warps
+        const int quarter = warp & 3;    // TMEM lane quarter this warp may read (warp id % 4)
+        const int chalf = warp >> 2;     // which half of the tile's columns this warp scans
+        float mx[8], sc[8];
+        int imx[8], isc[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) { mx[g] = 0.f; sc[g] = 0.f; imx[g] = -1; isc[g] = -1; }
+        for (int i = 0; i < n; i++) {
+            const int st = i % kStages, use = i / kStages;
+            mbar_wait(bar_mma(st), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // D[128 x BN] = sum over K chunks and 16-element K steps; one thread issues for the CTA
-            for (int c = 0; c < KCH; c++) {
-                const uint64_t da = umma_desc(smem_u32(sA + c * kBM * kSwizzleRow));
-                const uint64_t db = umma_desc(smem_u32(sB + c * BN * kSwizzleRow));
-#pragma unroll
-                for (int k = 0; k < 4; k++)  // +32 bytes (2 x 16 B units) per K step inside the swizzle row
-                    umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
-            }
-            umma_commit(bar_mma);  // arrives when the MMAs above have completed (implies before_thread_sync)
-        }
-        ph_load ^= 1;
-        mbar_wait(bar_mma, ph_mma);
-        ph_mma ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // epilogue: thread == (row = TMEM lane, half of the columns); 32 accumulator columns per tcgen05.ld.
-        // Branch-free running top-2 per group: values with max/min, indices with selects; the 8 groups
-        // of a 32-column chunk are independent dependency chains (ILP 8).
+            // thread == (row = TMEM lane, half of the columns); 32 accumulator columns per tcgen05.ld. Branch-free
+            // running top-2 per group: values with max/min, indices with selects; the 8 groups of a 32-column chunk
+            // are independent dependency chains (ILP 8).
 #pragma unroll 1
-        for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + cb, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int col0 = t * BN + cb;  // multiple of 32: group of column j is (j % 32) / 4
+            for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + st * BN + cb, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cb + 32 >= (chalf + 1) * (BN / 2)) {
+                    // last read of this accumulator by this warp: hand it back before the arithmetic
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free(st)) : "memory");
+                }
+                const int col0 = (t0 + i) * BN + cb;  // multiple of 32: group of column j is (j % 32) / 4
 #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const int g = j >> 2;
-                const float s = __uint_as_float(r[j]);
-                const bool gt1 = s > mx[g], gt2 = s > sc[g];
-                isc[g] = gt1 ? imx[g] : (gt2 ? col0 + j : isc[g]);
-                imx[g] = gt1 ? col0 + j : imx[g];
-                sc[g] = fmaxf(sc[g], fminf(mx[g], s));
-                mx[g] = fmaxf(mx[g], s);
+                for (int j = 0; j < 32; j++) {
+                    const int g = j >> 2;
+                    const float s = __uint_as_float(r[j]);
+                    const bool gt1 = s > mx[g], gt2 = s > sc[g];
+                    isc[g] = gt1 ? imx[g] : (gt2 ? col0 + j : isc[g]);
+                    imx[g] = gt1 ? col0 + j : imx[g];
+                    sc[g] = fmaxf(sc[g], fminf(mx[g], s));
+                    mx[g] = fmaxf(mx[g], s);
+                }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // TMEM and the B' buffers are free for the next tile
-    }
-    Top2* dst = part + ((size_t)(split * 2 + chalf) * n1pad + (size_t)rb * kBM + quarter * 32 + (tid & 31)) * 8;
+        Top2* dst = part + ((size_t)(split * 2 + chalf) * n1pad + (size_t)rb * kBM + quarter * 32 + lane) * 8;
 #pragma unroll
-    for (int g = 0; g < 8; g++) dst[g] = Top2{mx[g], sc[g], imx[g], isc[g]};
+        for (int g = 0; g < 8; g++)
+            reinterpret_cast<float4*>(dst)[g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(BN) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(Cfg::TMEM_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------- 3. exact re-score, group rule, merge
@@ -272,8 +302,12 @@ match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, c
         Top2 cs[8];
 #pragma unroll
         for (int u = 0; u < 8; u++)
-            cs[u] = s0 + u < nsplit ? part[((size_t)(s0 + u) * n1pad + p1) * 8 + g]  // 128 contiguous bytes per (split,row) across the warp
-                                    : Top2{0.f, 0.f, -1, -1};
+            if (s0 + u < nsplit) {  // 128 contiguous bytes per (split,row) across the warp, one 128-bit load per lane
+                const float4 w = __ldg(reinterpret_cast<const float4*>(part + ((size_t)(s0 + u) * n1pad + p1) * 8 + g));
+                cs[u] = Top2{w.x, w.y, __float_as_int(w.z), __float_as_int(w.w)};
+            } else {
+                cs[u] = Top2{0.f, 0.f, -1, -1};
+            }
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const float cv[2] = {cs[u].mx, cs[u].sc};
@@ -442,7 +476,7 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     if (!make_map(&mapA, ws.a, n1pad, Cfg::KTOT, kBM) || !make_map(&mapB, ws.b, n2pad, Cfg::KTOT, Cfg::BN)) return cudaErrorNotSupported;
     // per device (a process may hold contexts on several GPUs), so set on every launch
     if ((e = cudaFuncSetAttribute(match_mma<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
-    match_mma<NF><<<dim3(rbs, nsplit), 256, Cfg::SMEM, st>>>(mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
+    match_mma<NF><<<dim3(rbs, nsplit), (kEpiWarps + 1) * 32, Cfg::SMEM, st>>>(mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
     match_final<NF><<<(n1 + 3) / 4, 128, 0, st>>>(d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit * 2, n1pad);
     return cudaGetLastError();
 }
