@@ -401,8 +401,7 @@ extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
     // Chunk schedule: small chunks at both ends (the first upload and the last download are not hidden behind
     // anything), full chunks in between, alternating over two compute streams so that the tail of one chunk's
     // descriptor kernel overlaps the head of the next chunk.
-    int chunk = nframes >= 64 ? 16 : (nframes >= 32 ? 8 : (nframes >= 8 ? 4 : 1));
-    if (const char* e = getenv("SB_HOST_CHUNK")) chunk = std::max(1, atoi(e));  // tuning knob (experiments only)
+    const int chunk = nframes >= 64 ? 16 : (nframes >= 32 ? 8 : (nframes >= 8 ? 4 : 1));
     std::vector<int> first;  // first frame of every chunk, plus nframes
     {
         std::vector<int> sizes, tail;

@@ -16,8 +16,6 @@
 //   * descriptors leave the SM once, as 128-byte coalesced stores.
 // Arithmetic (rounding modes, FMA placement, IEEE division, __sinf/__cosf) follows the reference
 // so that descriptors agree to float round-off.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace sb {
@@ -609,7 +607,6 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     // live at a time (L2-resident) while still covering the machine for a single frame
     // (a single frame or a small batch fills the machine instead: 5 resident CTAs per SM)
     int ctas = sm_count * (nframes >= 5 ? 2 : (nframes >= 3 ? 3 : 5));
-    if (const char* e = getenv("SB_DESC_CTAS")) ctas = atoi(e);  // tuning knob (experiments only)
     if (ctas < 1) ctas = 1;
     if (ctas > need) ctas = need;
     const dim3 grid(ctas, nframes), block(kWarpsPerCta * 32);

@@ -17,4 +17,4 @@ for _ in range(3): det.detect_batch_host(hf, hp, hc, hd)
 torch.cuda.synchronize(); t0 = time.perf_counter(); N = 20
 for _ in range(N): det.detect_batch_host(hf, hp, hc, hd)
 torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / N
-print(f"chunk={os.environ.get('SB_HOST_CHUNK','default')} batch={B}: {dt*1e3:.3f} ms/step -> {B/dt:.0f} frames/s; kp/frame {hc.numpy().mean():.0f}")
+print(f"chunk={os.environ.get('SB_HOST_CHUNK_removed','default')} batch={B}: {dt*1e3:.3f} ms/step -> {B/dt:.0f} frames/s; kp/frame {hc.numpy().mean():.0f}")
