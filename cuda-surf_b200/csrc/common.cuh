@@ -34,6 +34,7 @@ struct OctaveP {
     int nmb;
     int hess_tile0, hess_tx, hess_ty;  // first linear tile id / tile grid of this octave (Hessian)
     int nms_tile0, nms_tx, nms_ty;     // same for the NMS cell grid (per z)
+    float inv_hess_tx, inv_nms_tx;     // 1 / hess_tx, 1 / nms_tx: tile decode without integer division (tile ids < 2^23)
 };
 
 struct PipeP {
@@ -97,6 +98,9 @@ __device__ __forceinline__ KpGeom kp_geom(float x, float y, float scale, int W, 
     g.e = 2 * g.step - g.S;
     return g;
 }
+// q = a / b for 0 <= a < 2^23 with inv = 1.f / b: exact (the +0.5 keeps the product away from the integer boundary)
+__device__ __forceinline__ int div_small(int a, float inv) { return __float2int_rz(__fmul_rn(__int2float_rn(a) + 0.5f, inv)); }
+
 // launchers (one translation unit per stage)
 cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_pitch, int w, int h, uint8_t* d_dst,
                               size_t dst_stride, int dst_pitch, int nframes, cudaStream_t st);

@@ -148,6 +148,8 @@ static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
         q.nms_ty = ch > 0 ? (ch + 7) / 8 : 0;
         if (q.nms_tx == 0 || q.nms_ty == 0) { q.nms_tx = 1; q.nms_ty = 1; }  // keep the tile table monotone
         nms_tiles += q.nmb * q.nms_tx * q.nms_ty;
+        q.inv_hess_tx = 1.f / (float)q.hess_tx;
+        q.inv_nms_tx = 1.f / (float)q.nms_tx;
         roff += (long long)P.max_scale * q.osz;
         octave += octave;
         sw >>= 1; sh >>= 1;

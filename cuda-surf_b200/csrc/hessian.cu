@@ -81,7 +81,7 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, f
     while (o + 1 < P.noctaves && tile >= P.oct[o + 1].hess_tile0) o++;
     const OctaveP& q = P.oct[o];
     const int lt = tile - q.hess_tile0;
-    const int ty = lt / q.hess_tx, tx = lt - ty * q.hess_tx;
+    const int ty = div_small(lt, q.inv_hess_tx), tx = lt - ty * q.hess_tx;
     const int ix = tx * 32 + threadIdx.x;
     if (ix >= q.sw) return;
     const int* I = Ibase + (size_t)f * P.istride + P.ip;

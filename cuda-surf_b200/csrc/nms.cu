@@ -123,9 +123,9 @@ nms_scan_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase
     const OctaveP& q = P.oct[o];
     int lt = tile - q.nms_tile0;
     const int per_z = q.nms_tx * q.nms_ty;
-    const int z = lt / per_z;
-    lt -= z * per_z;
-    const int ty = lt / q.nms_tx, tx = lt - ty * q.nms_tx;
+    int z = 0;
+    while (lt >= per_z) { lt -= per_z; z++; }  // z < nmb <= 3
+    const int ty = div_small(lt, q.inv_nms_tx), tx = lt - ty * q.nms_tx;
     const int lane = threadIdx.x;
     const int xc = tx * 32 + lane, yc = ty * 8 + threadIdx.y;
 
