@@ -41,12 +41,12 @@ def stage_sums(integral, layers):
     return out
 
 
-def run_case(name, img, outdir, noctaves, upright, extend=False, full=False, thresh=4.0, max_pts=65536):
+def run_case(name, img, outdir, noctaves, upright, extend=False, full=False, thresh=4.0, max_pts=65536, doubled=False):
     h, w = img.shape
-    ref = ref_lib.Reference(w, h, noctaves, thresh, False, 9, 2, upright, extend, 4)
+    ref = ref_lib.Reference(w, h, noctaves, thresh, doubled, 9, 2, upright, extend, 4)
     pts, desc = ref.detect(img, max_pts=max_pts, desc=True)
     d = {"w": w, "h": h, "noctaves": noctaves, "upright": int(upright), "extend": int(extend), "thresh": thresh,
-         "pts": pts, "npts": len(pts)}
+         "doubled": int(doubled), "pts": pts, "npts": len(pts)}
     if full:
         d["desc"] = desc
         integral, layers, _ = ref.stages(img)
@@ -67,6 +67,12 @@ def run_case(name, img, outdir, noctaves, upright, extend=False, full=False, thr
 def main():
     outdir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "golden")
     os.makedirs(outdir, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[2] == "doubled":
+        # doubled=true (surf.cpp:234-235): the reference's cuIntegralDoubleU4 path; added after the first set, so that
+        # the committed files of the other cases (nondeterministic keypoint order in the reference) stay as they are
+        run_case("small_doubled", sb.synth_frame(320, 240, 3), outdir, 3, True, full=True, doubled=True)
+        run_case("small_doubled_rotated", sb.synth_frame(200, 152, 5), outdir, 2, False, full=True, doubled=True)
+        return
     left = cv2.imread(os.path.join(HERE, "left_1280x960.png"), cv2.IMREAD_GRAYSCALE)
     right = cv2.imread(os.path.join(HERE, "right_1280x960.png"), cv2.IMREAD_GRAYSCALE)
     # config 1: main.cpp defaults (4 octaves, thresh 4, upright, 64-d), plus one rotated run

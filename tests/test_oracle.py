@@ -87,7 +87,8 @@ def test_match_semantics_small():
 
 
 GOLD = ["pair_left_upright", "pair_right_upright", "pair_left_rotated", "small_upright", "small_rotated",
-        "small_extend", "ragged_upright", "stereo_left", "stereo_right", "synth1080_upright"]
+        "small_extend", "ragged_upright", "stereo_left", "stereo_right", "synth1080_upright",
+        "small_doubled", "small_doubled_rotated"]
 
 
 def _image_for(name, g):
@@ -115,10 +116,11 @@ def test_oracle_against_reference_golden(name):
     h, w = img.shape
     assert (w, h) == (int(g["w"]), int(g["h"]))
     upright, extend, noct = bool(g["upright"]), bool(g["extend"]), int(g["noctaves"])
-    o = ol.Oracle(noct, float(g["thresh"]), False, 9, 2, upright, extend, 4)
+    doubled = bool(g["doubled"]) if "doubled" in g else False
+    o = ol.Oracle(noct, float(g["thresh"]), doubled, 9, 2, upright, extend, 4)
     I = o.integral(img)
     resp = o.hessian(I)
-    layers = o.split_resp(resp, w, h)
+    layers = o.split_resp(resp, I.shape[1] - 1, I.shape[0] - 1)  # the 2x frame when doubled
     if "integral" in g:
         assert np.array_equal(I, g["integral"])
         for k, L in enumerate(layers):
