@@ -1,7 +1,7 @@
 #!/bin/bash
 # per-kernel durations (ncu, no replay metrics) of the 64-frame batch: gpu_launchlist.sh <tag> [kernel regex]
 T=$1; K=${2:-.}
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" --csv --log-file gpurun_out/${T}_ll.csv python tools/prof_kernels.py 64 1 > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" --csv --log-file gpurun_out/${T}_ll.csv python tools/prof_kernels.py 64 ${UPR:-1} > /dev/null 2>&1
 python - <<PY
 import csv, collections
 rows = list(csv.reader(open('gpurun_out/${T}_ll.csv')))
