@@ -24,6 +24,22 @@
 
 using namespace sb;
 
+// one batch in flight on the host-buffer path: staging buffers, events and chunk schedule. Three sets: while batch k
+// downloads, batch k+1 computes and batch k+2 uploads.
+constexpr int kHostSets = 3;
+struct HostJob {
+    uint8_t* d_img = nullptr;
+    sb_point* d_pts = nullptr;
+    float* d_desc = nullptr;
+    int* d_counts = nullptr;
+    int* h_counts = nullptr;  // pinned
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaEvent_t ev_end[2] = {nullptr, nullptr};
+    std::vector<int> first;   // first frame of every chunk, plus nframes
+    int nframes = 0;
+    bool want_desc = false, active = false, submitted = false;
+};
+
 struct sb_ctx {
     sb_params prm{};
     PipeP P{};
@@ -31,7 +47,8 @@ struct sb_ctx {
     cudaStream_t stream = nullptr;
     // ingest / egress streams and per-chunk events of the pipelined host-buffer path (sb_detect_batch_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, stream2 = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_done;
+    HostJob job[kHostSets];
+    int next_set = 0;
     // scratch, `batch` frame slots each
     int* d_integral = nullptr;
     float* d_resp = nullptr;
@@ -42,10 +59,6 @@ struct sb_ctx {
     int cand_cap = 0;
     uint8_t* d_up = nullptr;  // doubled=true: the 2x up-sampled frames, `batch` slots of up_pitch * P.h bytes
     int up_pitch = 0;
-    // staging for the synchronous / host-buffer entry points
-    uint8_t* d_stage_img = nullptr;
-    sb_point* d_stage_pts = nullptr;
-    float* d_stage_desc = nullptr;
     int* h_counts = nullptr;          // pinned
     sb_point* h_pts = nullptr;        // pinned, max_pts
     MatchScratch match_ws;
@@ -172,14 +185,18 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_integral); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
-    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_stage_img); cudaFree(ctx->d_stage_pts);
-    cudaFree(ctx->d_stage_desc);
+    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); 
     free_match_scratch(ctx->match_ws);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
     if (ctx->h_match) cudaFreeHost(ctx->h_match);
-    for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
-    for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
+    for (HostJob& J : ctx->job) {
+        cudaFree(J.d_img); cudaFree(J.d_pts); cudaFree(J.d_desc); cudaFree(J.d_counts);
+        if (J.h_counts) cudaFreeHost(J.h_counts);
+        for (cudaEvent_t e : J.ev_in) cudaEventDestroy(e);
+        for (cudaEvent_t e : J.ev_done) cudaEventDestroy(e);
+        for (cudaEvent_t e : J.ev_end) if (e) cudaEventDestroy(e);
+    }
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -376,96 +393,146 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
     return SB_OK;
 }
 
-extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, sb_point* h_points, int* h_counts,
-                                    float* h_desc) {
+// ---- host-buffer path: submit / wait over two staging sets
+//
+// Pipelined ingest / compute / egress. A batch is cut into chunks; chunk k's frames go up on the ingest stream, its
+// kernels run on a compute stream behind an event, and as soon as its keypoint counts are visible on the host the
+// exact-size copies of its points and descriptors are queued on the egress stream -- so the H2D of chunk k+1, the
+// kernels of chunk k and the D2H of chunk k-1 overlap (two copy engines, PCIe is full duplex). The reference does all of
+// this serially per frame with blocking copies (main.cpp:211-226, surf.cpp:302-303, 335-342).
+// Chunk schedule: small chunks at both ends (the first upload and the last download are not hidden behind anything),
+// full chunks in between, alternating over two compute streams so that the tail of one chunk's descriptor kernel
+// overlaps the head of the next chunk. With submit / wait the caller keeps up to three batches in flight (three sets of
+// staging buffers and events): batch k downloads while batch k+1 computes and batch k+2 uploads.
+// streaming: another batch is in flight, so this batch's first upload and the other's last download are already hidden;
+// one chunk on one compute stream (the kernels are most efficient on many frames, and two interleaved streams cost 10 %).
+static void chunk_schedule(int nframes, bool streaming, std::vector<int>& first) {
+    const int chunk = streaming ? nframes : (nframes >= 64 ? 16 : (nframes >= 32 ? 8 : (nframes >= 8 ? 4 : 1)));
+    std::vector<int> sizes, tail;
+    int left = nframes;
+    for (int r = 2; !streaming && r < chunk && left > 2 * chunk; r *= 2) { sizes.push_back(r); tail.push_back(r); left -= 2 * r; }
+    while (left > 0) { const int c = std::min(chunk, left); sizes.push_back(c); left -= c; }
+    for (int i = (int)tail.size() - 1; i >= 0; i--) sizes.push_back(tail[i]);
+    first.clear();
+    int f = 0;
+    for (int c : sizes) { first.push_back(f); f += c; }
+    first.push_back(f);
+}
+
+extern "C" int sb_submit_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, int want_desc, int* ticket) {
     if (!ctx) return SB_ERR_INVALID;
     const PipeP& P = ctx->P;
-    if (!h_images || !h_points || !h_counts || nframes < 1 || nframes > ctx->prm.batch)
-        return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_host: bad argument");
+    if (!h_images || !ticket || nframes < 1 || nframes > ctx->prm.batch)
+        return fail(ctx, SB_ERR_INVALID, "sb_submit_batch_host: bad argument");
+    const int set = ctx->next_set;
+    HostJob& J = ctx->job[set];
+    if (J.active) return fail(ctx, SB_ERR_INVALID, "sb_submit_batch_host: three batches are already in flight; call sb_wait_batch_host first");
     CU(cudaSetDevice(ctx->device));
     const int B = ctx->prm.batch;
     const int sw_ = ctx->prm.width, sh_ = ctx->prm.height;  // the caller's frame size (P.w, P.h are the 2x size if doubled)
     const size_t fbytes = (size_t)sw_ * sh_;
     const int dpitch = align_up(sw_, 128);
     const size_t dstride = (size_t)dpitch * sh_;
-    if (!ctx->d_stage_img) {
-        CU(cudaMalloc((void**)&ctx->d_stage_img, dstride * B));
-        CU(cudaMemset(ctx->d_stage_img, 0, dstride * B));
-        CU(cudaMalloc((void**)&ctx->d_stage_pts, sizeof(sb_point) * (size_t)P.max_pts * B));
-        CU(cudaMalloc((void**)&ctx->d_stage_desc, sizeof(float) * (size_t)P.max_pts * P.nfeatures * B));
-    }
-    // Pipelined ingest / compute / egress. The batch is cut into chunks; chunk k's frames go up on the
-    // ingest stream, its kernels run on the compute stream behind an event, and as soon as its keypoint
-    // counts are visible on the host the exact-size copies of its points and descriptors are queued on
-    // the egress stream -- so the H2D of chunk k+1, the kernels of chunk k and the D2H of chunk k-1
-    // overlap (two copy engines, PCIe is full duplex). The reference does all of this serially per frame
-    // with blocking copies (main.cpp:211-226, surf.cpp:302-303, 335-342).
-    // Chunk schedule: small chunks at both ends (the first upload and the last download are not hidden behind
-    // anything), full chunks in between, alternating over two compute streams so that the tail of one chunk's
-    // descriptor kernel overlaps the head of the next chunk.
-    const int chunk = nframes >= 64 ? 16 : (nframes >= 32 ? 8 : (nframes >= 8 ? 4 : 1));
-    std::vector<int> first;  // first frame of every chunk, plus nframes
-    {
-        std::vector<int> sizes, tail;
-        int left = nframes;
-        for (int r = 2; r < chunk && left > 2 * chunk; r *= 2) { sizes.push_back(r); tail.push_back(r); left -= 2 * r; }
-        while (left > 0) { const int c = std::min(chunk, left); sizes.push_back(c); left -= c; }
-        for (int i = (int)tail.size() - 1; i >= 0; i--) sizes.push_back(tail[i]);
-        int f = 0;
-        for (int c : sizes) { first.push_back(f); f += c; }
-        first.push_back(f);
-    }
-    const int nchunks = (int)first.size() - 1;
     if (!ctx->s_h2d) {
         CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     }
-    while ((int)ctx->ev_in.size() < nchunks) {
+    if (!J.d_img) {
+        CU(cudaMalloc((void**)&J.d_img, dstride * B));
+        CU(cudaMemset(J.d_img, 0, dstride * B));
+        CU(cudaMalloc((void**)&J.d_pts, sizeof(sb_point) * (size_t)P.max_pts * B));
+        CU(cudaMalloc((void**)&J.d_desc, sizeof(float) * (size_t)P.max_pts * P.nfeatures * B));
+        CU(cudaMalloc((void**)&J.d_counts, sizeof(int) * B));
+        CU(cudaMallocHost((void**)&J.h_counts, sizeof(int) * B));
+        CU(cudaEventCreateWithFlags(&J.ev_end[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&J.ev_end[1], cudaEventDisableTiming));
+    }
+    bool streaming = false;
+    for (int k = 0; k < kHostSets; k++) streaming |= k != set && ctx->job[k].active;
+    chunk_schedule(nframes, streaming, J.first);
+    const int nchunks = (int)J.first.size() - 1;
+    while ((int)J.ev_in.size() < nchunks) {
         cudaEvent_t a = nullptr, b = nullptr;
         CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        ctx->ev_in.push_back(a);
+        J.ev_in.push_back(a);
         CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        ctx->ev_done.push_back(b);
+        J.ev_done.push_back(b);
+    }
+    // The previously submitted batch shares the scratch slots (integral, responses, candidate queues) of this one. Chunk
+    // c of both runs on the same compute stream when their schedules are equal; otherwise order them explicitly.
+    HostJob& O = ctx->job[(set + kHostSets - 1) % kHostSets];
+    if (O.submitted && (O.nframes != nframes || O.first != J.first)) {
+        for (cudaStream_t st : {ctx->stream, ctx->stream2}) {
+            CU(cudaStreamWaitEvent(st, O.ev_end[0], 0));
+            CU(cudaStreamWaitEvent(st, O.ev_end[1], 0));
+        }
     }
     const size_t pstride = (size_t)P.max_pts, dstride_f = (size_t)P.max_pts * P.nfeatures;
     for (int k = 0; k < nchunks; k++) {
-        const int f0 = first[k], nf = first[k + 1] - f0;
+        const int f0 = J.first[k], nf = J.first[k + 1] - f0;
         cudaStream_t st = (k & 1) ? ctx->stream2 : ctx->stream;
         if (dpitch == sw_) {
-            CU(cudaMemcpyAsync(ctx->d_stage_img + f0 * dstride, h_images + f0 * fbytes, fbytes * nf, cudaMemcpyHostToDevice, ctx->s_h2d));
+            CU(cudaMemcpyAsync(J.d_img + f0 * dstride, h_images + f0 * fbytes, fbytes * nf, cudaMemcpyHostToDevice, ctx->s_h2d));
         } else {
             for (int f = f0; f < f0 + nf; f++)
-                CU(cudaMemcpy2DAsync(ctx->d_stage_img + f * dstride, dpitch, h_images + f * fbytes, sw_, sw_, sh_,
-                                     cudaMemcpyHostToDevice, ctx->s_h2d));
+                CU(cudaMemcpy2DAsync(J.d_img + f * dstride, dpitch, h_images + f * fbytes, sw_, sw_, sh_, cudaMemcpyHostToDevice, ctx->s_h2d));
         }
-        CU(cudaEventRecord(ctx->ev_in[k], ctx->s_h2d));
-        CU(cudaStreamWaitEvent(st, ctx->ev_in[k], 0));
-        const int rc = enqueue_frames(ctx, ctx->d_stage_img + f0 * dstride, dstride, dpitch, nf, ctx->d_stage_pts + f0 * pstride,
-                                      ctx->d_counts + f0, h_desc ? ctx->d_stage_desc + f0 * dstride_f : nullptr, st, nullptr, f0);
+        CU(cudaEventRecord(J.ev_in[k], ctx->s_h2d));
+        CU(cudaStreamWaitEvent(st, J.ev_in[k], 0));
+        const int rc = enqueue_frames(ctx, J.d_img + f0 * dstride, dstride, dpitch, nf, J.d_pts + f0 * pstride, J.d_counts + f0,
+                                      want_desc ? J.d_desc + f0 * dstride_f : nullptr, st, nullptr, f0);
         if (rc != SB_OK) return rc;
-        // counts land in the context's pinned array (the caller's may be pageable, which would block here)
-        CU(cudaMemcpyAsync(ctx->h_counts + f0, ctx->d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(ctx->ev_done[k], st));
+        // counts land in pinned memory of the set (the caller's array may be pageable, which would block here)
+        CU(cudaMemcpyAsync(J.h_counts + f0, J.d_counts + f0, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(J.ev_done[k], st));
     }
+    CU(cudaEventRecord(J.ev_end[0], ctx->stream));
+    CU(cudaEventRecord(J.ev_end[1], ctx->stream2));
+    J.nframes = nframes; J.want_desc = want_desc != 0; J.active = true; J.submitted = true;
+    *ticket = set;
+    ctx->next_set = (set + 1) % kHostSets;
+    return SB_OK;
+}
+
+extern "C" int sb_wait_batch_host(sb_ctx* ctx, int ticket, sb_point* h_points, int* h_counts, float* h_desc) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (ticket < 0 || ticket >= kHostSets || !ctx->job[ticket].active || !h_points || !h_counts)
+        return fail(ctx, SB_ERR_INVALID, "sb_wait_batch_host: bad ticket or argument");
+    HostJob& J = ctx->job[ticket];
+    if (h_desc && !J.want_desc) return fail(ctx, SB_ERR_INVALID, "sb_wait_batch_host: the batch was submitted without descriptors");
+    const PipeP& P = ctx->P;
+    CU(cudaSetDevice(ctx->device));
+    const size_t pstride = (size_t)P.max_pts, dstride_f = (size_t)P.max_pts * P.nfeatures;
+    const int nchunks = (int)J.first.size() - 1;
+    J.active = false;
     for (int k = 0; k < nchunks; k++) {
-        const int f0 = first[k], nf = first[k + 1] - f0;
-        CU(cudaEventSynchronize(ctx->ev_done[k]));  // counts of chunk k are on the host; later chunks keep running
-        CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[k], 0));
+        const int f0 = J.first[k], nf = J.first[k + 1] - f0;
+        CU(cudaEventSynchronize(J.ev_done[k]));  // counts of chunk k are on the host; later chunks keep running
+        CU(cudaStreamWaitEvent(ctx->s_d2h, J.ev_done[k], 0));
         for (int f = f0; f < f0 + nf; f++) {
-            const int n = h_counts[f] = ctx->h_counts[f];
+            const int n = h_counts[f] = J.h_counts[f];
             if (n <= 0) continue;  // only the keypoints that exist travel
-            CU(cudaMemcpyAsync(h_points + f * pstride, ctx->d_stage_pts + f * pstride, sizeof(sb_point) * n,
-                               cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CU(cudaMemcpyAsync(h_points + f * pstride, J.d_pts + f * pstride, sizeof(sb_point) * n, cudaMemcpyDeviceToHost, ctx->s_d2h));
             if (h_desc)
-                CU(cudaMemcpyAsync(h_desc + f * dstride_f, ctx->d_stage_desc + f * dstride_f,
-                                   sizeof(float) * (size_t)n * P.nfeatures, cudaMemcpyDeviceToHost, ctx->s_d2h));
+                CU(cudaMemcpyAsync(h_desc + f * dstride_f, J.d_desc + f * dstride_f, sizeof(float) * (size_t)n * P.nfeatures,
+                                   cudaMemcpyDeviceToHost, ctx->s_d2h));
         }
     }
     CU(cudaStreamSynchronize(ctx->s_d2h));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream2));
     return SB_OK;
+}
+
+extern "C" int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, sb_point* h_points, int* h_counts,
+                                    float* h_desc) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (!h_points || !h_counts) return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_host: bad argument");
+    for (const HostJob& J : ctx->job)
+        if (J.active) return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_host: a submitted batch is still in flight");
+    int ticket = -1;
+    const int rc = sb_submit_batch_host(ctx, h_images, nframes, h_desc != nullptr, &ticket);
+    if (rc != SB_OK) return rc;
+    return sb_wait_batch_host(ctx, ticket, h_points, h_counts, h_desc);
 }
 
 static int match_args_ok(sb_ctx* ctx, sb_point* d_pts1, int n1, const float* d_feat1, const sb_point* d_pts2, int n2,

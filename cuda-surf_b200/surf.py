@@ -171,6 +171,19 @@ class Surfor:
                                           _hptr(desc))
         B.check(rc, self._ctx)
 
+    def submit_batch_host(self, frames, want_desc=True):
+        """First half of detect_batch_host: uploads + kernels of a batch are enqueued, a ticket comes back. At most two
+        batches may be outstanding; `frames` must stay alive until the ticket has been waited for."""
+        t = C.c_int(-1)
+        rc = B.lib().sb_submit_batch_host(self._ctx, _hptr(frames), frames.shape[0], int(want_desc), C.byref(t))
+        B.check(rc, self._ctx)
+        return t.value
+
+    def wait_batch_host(self, ticket, points, counts, desc=None):
+        """Second half: downloads the batch's counts, points and descriptors into the host buffers."""
+        rc = B.lib().sb_wait_batch_host(self._ctx, ticket, _hptr(points), _hptr(counts), _hptr(desc))
+        B.check(rc, self._ctx)
+
     # ---- stage access (parity tests) ------------------------------------------------------------
     def get_integral(self, slot=0):
         out = np.empty((self.info.ih, self.info.iw), np.int32)

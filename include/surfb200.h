@@ -130,6 +130,12 @@ int sb_detect_batch_async(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
  * and descriptors, synchronised on return. h_images tight (pitch == width).                   */
 int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, sb_point* h_points, int* h_counts,
                          float* h_desc);
+/* The same in two halves, for a caller that streams batches: sb_submit_batch_host enqueues the uploads and kernels of a
+ * batch and returns a ticket (at most three outstanding); sb_wait_batch_host downloads that batch's counts, points and
+ * descriptors and returns when they are in the caller's buffers. With two batches submitted ahead, batch k downloads
+ * while batch k+1 computes and batch k+2 uploads. h_images must stay valid until the ticket has been waited for.     */
+int sb_submit_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, int want_desc, int* ticket);
+int sb_wait_batch_host(sb_ctx* ctx, int ticket, sb_point* h_points, int* h_counts, float* h_desc);
 int sb_sync(sb_ctx* ctx);
 /* Same work as sb_detect_batch_async, synchronous, with CUDA events recorded on the launching stream
  * at the stage boundaries: stage_ms[0..3] = integral, Hessian, NMS+refine(+clamp), orientation+describe.

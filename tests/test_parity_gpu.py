@@ -361,6 +361,28 @@ def test_batch_equals_single_and_host_path():
     det.detect_batch_host(torch.from_numpy(frames).pin_memory()[:3], hp2, hc2, None)
     assert np.array_equal(hc2.numpy()[:3], counts[:3])
     assert np.array_equal(np.sort(hp2[1].numpy().view(sb.POINT_DTYPE)[: counts[1]]["x"]), np.sort(hp[1, : counts[1]]["x"]))
+    # several batches in flight (submit / wait): different sizes, results equal to the synchronous call
+    fa, fb = np.ascontiguousarray(frames[:9]), np.ascontiguousarray(frames[2:7])
+    ta = det.submit_batch_host(fa)
+    tb = det.submit_batch_host(fb)
+    td = det.submit_batch_host(fb)
+    with pytest.raises(sb.SurfError):
+        det.submit_batch_host(fa)  # a fourth outstanding batch is refused
+    pa, ca, da = np.zeros((9, 4096), sb.POINT_DTYPE), np.zeros(9, np.int32), np.zeros((9, 4096, 64), np.float32)
+    pb, cb, db = np.zeros((5, 4096), sb.POINT_DTYPE), np.zeros(5, np.int32), np.zeros((5, 4096, 64), np.float32)
+    det.wait_batch_host(ta, pa, ca, da)
+    tc = det.submit_batch_host(fa)  # the first set is free again
+    det.wait_batch_host(tb, pb, cb, db)
+    pc, cc, dc = np.zeros((9, 4096), sb.POINT_DTYPE), np.zeros(9, np.int32), np.zeros((9, 4096, 64), np.float32)
+    det.wait_batch_host(td, pb.copy(), cb.copy(), None)
+    det.wait_batch_host(tc, pc, cc, dc)
+    assert np.array_equal(ca, counts) and np.array_equal(cb, counts[2:7]) and np.array_equal(cc, counts)
+    for f in range(5):
+        n = counts[2 + f]
+        o1 = np.argsort(pb[f, :n], order=["x", "y", "scale"]); o2 = np.argsort(hp[2 + f, :n], order=["x", "y", "scale"])
+        assert np.array_equal(pb[f, :n]["x"][o1], hp[2 + f, :n]["x"][o2]) and np.array_equal(db[f, :n][o1], hd[2 + f, :n][o2])
+        o3 = np.argsort(pc[2 + f, :n], order=["x", "y", "scale"])
+        assert np.array_equal(dc[2 + f, :n][o3], hd[2 + f, :n][o2])
     single = make_det(w, h, 4, max_pts=4096)
     for f in range(nb):
         data, spts, sdesc = run_detect(single, frames[f], max_pts=4096)
