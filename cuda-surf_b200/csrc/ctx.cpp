@@ -124,6 +124,7 @@ static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
     for (int o = 0; o < P.noctaves; o++) {
         OctaveP& q = P.oct[o];
         if (sw < 1 || sh < 1) { why = "too many octaves for this frame size"; return SB_ERR_INVALID; }
+        if (sw > 8191 || sh > 8191) { why = "response map wider than 8191 samples (the NMS candidate queue packs row and column into 13 bits each)"; return SB_ERR_INVALID; }
         q.sw = sw; q.sh = sh; q.sp = align_up(sw, 128); q.osz = q.sh * q.sp;
         q.octave = octave; q.delta = P.sampling * octave; q.resp_off = roff;
         if (o > 0) {

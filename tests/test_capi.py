@@ -56,6 +56,7 @@ def test_create_fails_loudly_without_gpu():
     (dict(desc_wsz=5), B.SB_ERR_INVALID),
     (dict(width=4000, height=3000), B.SB_ERR_INVALID),  # int32 integral would overflow
     (dict(noctaves=8, width=64, height=64), B.SB_ERR_INVALID),
+    (dict(width=20000, height=400), B.SB_ERR_INVALID),  # 10000 response columns do not fit the packed candidate word
 ])
 def test_parameter_validation(kw, code):
     args = dict(noctaves=4, thresh=4.0, doubled=False, init_mask_size=9, sampling_step=2, upright=True, extend=False,
