@@ -206,8 +206,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
 }
 
 extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
-    sb_ctx* ctx = nullptr;  // errors before allocation go to the thread-local slot
-    if (!out || !params) return fail(nullptr, SB_ERR_INVALID, "null argument");
+    if (!out || !params) return fail(nullptr, SB_ERR_INVALID, "null argument");  // (errors of sb_create go to the thread-local slot)
     *out = nullptr;
     PipeP P;
     std::string why;
@@ -265,7 +264,6 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
         sb_destroy(c);
         return e == cudaErrorMemoryAllocation ? SB_ERR_NOMEM : SB_ERR_CUDA;
     }
-    (void)ctx;
     *out = c;
     return SB_OK;
 }
@@ -282,7 +280,10 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
         t += (long long)P.max_scale * P.oct[o].sw * P.oct[o].sh;
     }
     info->resp_floats = t;
-    info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + 2 /*hessian*/ + 2 /*nms*/ + 1 /*clamp*/ + (P.upright ? 1 : 2);
+    // (the octave-0 shared-memory Hessian kernel exists for the reference's default geometry only, hessian.cu)
+    const bool fast0 = P.sampling == 2 && P.init_lobe == 3 && P.max_scale == 5;
+    const int nhess = fast0 ? (P.noctaves > 1 ? 2 : 1) : 1;
+    info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + nhess + 2 /*nms scan, refine*/ + 1 /*clamp*/ + (P.upright ? 1 : 2);
     return SB_OK;
 }
 
