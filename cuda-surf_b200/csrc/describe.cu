@@ -257,12 +257,14 @@ __device__ __forceinline__ void place(float* __restrict__ h, int lane, int W, in
     }
 }
 
+// Rotated descriptor (describeApproxWithoutNormalization + addSample, surfd.cu:2391-2444, 1984-2015): the sampling lattice
+// stays axis-aligned in the image, the window coordinates (rpos, cpos) are rotated by the keypoint's orientation, so rows
+// and columns do not separate as in the upright kernel; a warp walks the (2R+1)^2 lattice 32 samples at a time.
 // grid (ctas, nframes), 4 warps per CTA, dynamic smem = 4 * NF*32 floats + 40 floats.
-template <bool UPRIGHT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-describe_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
-                long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
-                long long desc_stride) {
+describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
+                        long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
+                        long long desc_stride) {
     extern __shared__ float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz, O = P.orient_size;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,32 +290,25 @@ describe_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, 
         const int S = __float2int_rz(sc);
         const float wofs = __fmaf_rn(fW, 0.5f, -0.5f);
         const float fstep = __int2float_rn(step);
-        float sine = 0.f, cose = 1.f, fracr = fy, fracc = fx;
-        int R;
-        if (UPRIGHT) {
-            R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(spacing, __int2float_rn(W + 1)), 0.5f), fstep));
-        } else {
-            const float ori = pts[pi].ori;
-            sine = __sinf(ori);
-            cose = __cosf(ori);
-            fracc = __fmaf_rn(-sine, fy, __fmul_rn(cose, fx));
-            fracr = __fmaf_rn(cose, fy, __fmul_rn(sine, fx));
-            R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(1.4f, spacing), __int2float_rn(W + 1)), 0.5f), fstep));
-        }
+        const float ori = pts[pi].ori;
+        const float sine = __sinf(ori), cose = __cosf(ori);
+        const float fracc = __fmaf_rn(-sine, fy, __fmul_rn(cose, fx));
+        const float fracr = __fmaf_rn(cose, fy, __fmul_rn(sine, fx));
+        const int R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(1.4f, spacing), __int2float_rn(W + 1)), 0.5f), fstep));
         const int side = 2 * R + 1, total = side * side;
         const float inv_side = 1.f / (float)side;
+        // |rpos| < (W+1)/2 is the window test -1 < rpos + wofs < W; about half of the lattice (the corners of the bounding
+        // square of the rotated window) fails it by a wide margin and is rejected on the numerators, before the two IEEE
+        // divisions. The margin keeps the exact test below the only one that decides.
+        const float far_lim = __fmul_rn(__fmaf_rn(fW, 0.5f, 0.51f), spacing);
         for (int qi = lane; qi < total; qi += 32) {
             const int ii = (int)(((float)qi + 0.5f) * inv_side);
             const int i = ii - R, j = qi - ii * side - R;
-            float rpos, cpos;
-            if (UPRIGHT) {
-                rpos = __fdiv_rn(__fsub_rn(__int2float_rn(step * i), fy), spacing);
-                cpos = __fdiv_rn(__fsub_rn(__int2float_rn(step * j), fx), spacing);
-            } else {
-                const float fi = __int2float_rn(i), fj = __int2float_rn(j);
-                rpos = __fdiv_rn(__fmaf_rn(fstep, __fmaf_rn(cose, fi, __fmul_rn(sine, fj)), -fracr), spacing);
-                cpos = __fdiv_rn(__fmaf_rn(fstep, __fmaf_rn(-sine, fi, __fmul_rn(cose, fj)), -fracc), spacing);
-            }
+            const float fi = __int2float_rn(i), fj = __int2float_rn(j);
+            const float nr = __fmaf_rn(fstep, __fmaf_rn(cose, fi, __fmul_rn(sine, fj)), -fracr);
+            const float nc = __fmaf_rn(fstep, __fmaf_rn(-sine, fi, __fmul_rn(cose, fj)), -fracc);
+            if (fabsf(nr) > far_lim || fabsf(nc) > far_lim) continue;
+            const float rpos = __fdiv_rn(nr, spacing), cpos = __fdiv_rn(nc, spacing);
             const float rx = __fadd_rn(rpos, wofs), cx = __fadd_rn(cpos, wofs);
             if (!(rx > -1.f && rx < fW && cx > -1.f && cx < fW)) continue;
             const int r = iyc + i * step, c = ixc + j * step;
@@ -321,11 +316,8 @@ describe_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, 
             const float weight = s_lut2[__float2int_rz(__fmaf_rn(rpos, rpos, __fmul_rn(cpos, cpos)))];
             const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_x(I, P.ip, c, r, S))), kR255);
             const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_y(I, P.ip, c, r, S))), kR255);
-            float dx = a, dy = b;
-            if (!UPRIGHT) {
-                dx = __fmaf_rn(cose, a, __fmul_rn(sine, b));
-                dy = __fmaf_rn(sine, a, -__fmul_rn(cose, b));
-            }
+            const float dx = __fmaf_rn(cose, a, __fmul_rn(sine, b));
+            const float dy = __fmaf_rn(sine, a, -__fmul_rn(cose, b));
             if (O == 4) {
                 place(h, lane, W, O, dx, (dx < 0.f ? 0 : 1), dy, (dy < 0.f ? 2 : 3), rx, cx);
             } else {
@@ -622,8 +614,8 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
         }
     } else {
         const size_t smem = ((size_t)kWarpsPerCta * P.nfeatures * 32 + 40) * sizeof(float);
-        cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        describe_kernel<false><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+        cudaFuncSetAttribute(describe_rotated_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        describe_rotated_kernel<<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
     }
     return cudaGetLastError();
 }
