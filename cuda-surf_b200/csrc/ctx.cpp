@@ -61,6 +61,11 @@ struct sb_ctx {
     int up_pitch = 0;
     int* h_counts = nullptr;          // pinned
     sb_point* h_pts = nullptr;        // pinned, max_pts
+    // sb_detect_and_compute replays one captured CUDA graph per (image, points, descriptor) pointer set: the eight launches,
+    // the counter memset and the two result copies of a frame go down as one submission
+    struct FrameGraph { const void* img; int pitch; void* pts; void* desc; int spec; cudaGraphExec_t exec; };
+    std::vector<FrameGraph> graphs;
+    bool graphs_ok = true;
     MatchScratch match_ws;
     sb_point* h_match = nullptr;      // pinned staging of sb_match's host copy
     size_t h_match_cap = 0;
@@ -187,6 +192,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_integral); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
     cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); 
+    for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     free_match_scratch(ctx->match_ws);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
     if (ctx->h_pts) cudaFreeHost(ctx->h_pts);
@@ -379,15 +385,58 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
         d_desc = *d_desc_addr;
     }
     cudaStream_t st = ctx->stream;
-    const int rc = enqueue_frames(ctx, d_image, 0, pitch, 1, d_points, ctx->d_counts, d_desc, st);
-    if (rc != SB_OK) return rc;
-    CU(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // One host round trip instead of two: the first kSpec points travel with the count (5 k keypoints are typical at
+    // 1080p, so the copy is rarely longer than needed by more than 0.2 MB); a frame with more gets the rest afterwards.
+    constexpr int kSpec = 8192;
+    const int spec = h_points ? std::min(P.max_pts, kSpec) : 0;
+    auto enqueue_all = [&]() -> int {
+        const int rc = enqueue_frames(ctx, d_image, 0, pitch, 1, d_points, ctx->d_counts, d_desc, st);
+        if (rc != SB_OK) return rc;
+        CU(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (spec > 0) CU(cudaMemcpyAsync(ctx->h_pts, d_points, sizeof(sb_point) * (size_t)spec, cudaMemcpyDeviceToHost, st));
+        return SB_OK;
+    };
+    bool launched = false;
+    if (ctx->graphs_ok) {
+        sb_ctx::FrameGraph* hit = nullptr;
+        for (auto& g : ctx->graphs)
+            if (g.img == d_image && g.pitch == pitch && g.pts == d_points && g.desc == d_desc && g.spec == spec) { hit = &g; break; }
+        if (!hit && ctx->graphs.size() < 16) {
+            // capture this pointer set once (the demo loop of main.cpp:239-245 alternates between two)
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                const int rc = enqueue_all();
+                ok = cudaStreamEndCapture(st, &graph) == cudaSuccess && rc == SB_OK && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) {
+                ctx->graphs.push_back({d_image, pitch, d_points, d_desc, spec, exec});
+                hit = &ctx->graphs.back();
+            } else {
+                cudaGetLastError();      // clear; fall back to plain launches for good
+                ctx->graphs_ok = false;
+            }
+        }
+        if (hit && ctx->graphs_ok) {
+            CU(cudaGraphLaunch(hit->exec, st));
+            launched = true;
+        }
+    }
+    if (!launched) {
+        const int rc = enqueue_all();
+        if (rc != SB_OK) return rc;
+    }
     CU(cudaStreamSynchronize(st));
     const int n = ctx->h_counts[0];
     *num_pts = n;
     if (h_points && n > 0) {
-        CU(cudaMemcpyAsync(ctx->h_pts, d_points, sizeof(sb_point) * (size_t)n, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        if (n > spec) {
+            CU(cudaMemcpyAsync(ctx->h_pts + spec, d_points + spec, sizeof(sb_point) * (size_t)(n - spec), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
         // the reference copies the first 6 (7 with orientation) 4-byte fields of each point, surf.cpp:339
         // (two loops with compile-time sizes: the copies inline to a few moves instead of 5 k memcpy calls)
         if (want_desc && !P.upright) for (int i = 0; i < n; i++) std::memcpy(&h_points[i], &ctx->h_pts[i], 7 * sizeof(float));
