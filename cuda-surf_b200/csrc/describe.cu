@@ -385,6 +385,9 @@ __device__ __forceinline__ void emit_row(float* __restrict__ h, int lane, int W,
     }
 }
 
+struct TrueT { static constexpr bool value = true; };
+struct FalseT { static constexpr bool value = false; };
+
 template <int O>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
 describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
@@ -399,6 +402,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     for (int t = threadIdx.x; t < 40; t += blockDim.x) s_lut2[t] = P.lut2[t];
     __syncthreads();
     float* h = smem + warp * NF * 32;
+    const unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut2);
     const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
     const int ip = P.ip;
     const int* I = Ibase + (size_t)f * P.istride + ip;
@@ -504,7 +508,10 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                 int ii = row_lo + half;
                 int seg = 0, segend = row_lo + segcnt[0];
                 // one sample: prev = row two lattice steps up (its X row is this row's m, its q row this row's Y)
-                auto sample = [&](const RowSet& prev, const RowSet& cur, RowSet& next) {
+                // `carry` is uniform over the warp (one keypoint), so it selects one of two instantiations of the sweep:
+                // as a run-time predicate the re-read of the generic case cost 17 issue slots per sample even when off.
+                auto sample = [&](auto carry_tag, const RowSet& prev, const RowSet& cur, RowSet& next) {
+                    constexpr bool kCarry = decltype(carry_tag)::value;
                     if (ii + 2 * kAhead < row_hi) gather8(ii + 2 * kAhead, next);
                     while (ii >= segend) {  // the rows of cell row seg-1 are done: flush it, the upper half moves down
                         if (seg >= 1) flush(seg - 1, lo, xlo);
@@ -516,13 +523,14 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                         segend = seg <= W ? row_lo + cnt : (1 << 30);
                     }
                     int m0 = prev.g[0], m1 = prev.g[1], m2 = prev.g[2], m3 = prev.g[3], yA = prev.g[4], yD = prev.g[7];
-                    if (!carry) {
+                    if (!kCarry) {
                         // generic (S, step): rows z = r and u = r+1 were gathered as X and Y, m is re-read
                         const int om = cur.rowoff - sip, oy = cur.rowoff + offY;
                         m0 = __ldg(pA + om); m1 = __ldg(pB + om); m2 = __ldg(pB + om + 1); m3 = __ldg(pD + om);
                         yA = __ldg(pA + oy); yD = __ldg(pD + oy);
                     }
-                    const float weight = s_lut2[__float2int_rz(__fmaf_rn(cur.rpos, cur.rpos, cpos2))];
+                    float weight;
+                    asm("ld.shared.f32 %0, [%1];" : "=f"(weight) : "r"(lut_sa + 4u * (unsigned)__float2int_rz(__fmaf_rn(cur.rpos, cur.rpos, cpos2))));
                     const int wx = (cur.g[7] + m1 - m3 - cur.g[5]) - (cur.g[6] + m0 - m2 - cur.g[4]);
                     const int wy = (cur.g[3] - cur.g[0]) + (yD - yA) - (m3 - m0) - (cur.g[7] - cur.g[4]);
                     const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(wx)), kR255);
@@ -551,10 +559,18 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                         r0.g[4] = __ldg(pA + oy); r0.g[7] = __ldg(pD + oy); r0.g[5] = 0; r0.g[6] = 0;
                         r0.rpos = 0.f; r0.w0 = 0.f; r0.w1 = 0.f; r0.rowoff = 0;
                     }
-                    while (true) {
-                        sample(r0, r1, r2); if (ii >= row_hi) break;
-                        sample(r1, r2, r0); if (ii >= row_hi) break;
-                        sample(r2, r0, r1); if (ii >= row_hi) break;
+                    if (carry) {
+                        while (true) {
+                            sample(TrueT{}, r0, r1, r2); if (ii >= row_hi) break;
+                            sample(TrueT{}, r1, r2, r0); if (ii >= row_hi) break;
+                            sample(TrueT{}, r2, r0, r1); if (ii >= row_hi) break;
+                        }
+                    } else {
+                        while (true) {
+                            sample(FalseT{}, r0, r1, r2); if (ii >= row_hi) break;
+                            sample(FalseT{}, r1, r2, r0); if (ii >= row_hi) break;
+                            sample(FalseT{}, r2, r0, r1); if (ii >= row_hi) break;
+                        }
                     }
                     // the last row's cell rows: ri = seg-1 (lo) and ri+1 (hi)
                     if (seg >= 1) flush(seg - 1, lo, xlo);

@@ -37,16 +37,13 @@ __device__ __forceinline__ void load_shifted(const uint8_t* __restrict__ row, in
     }
     unsigned prev = __shfl_up_sync(0xffffffffu, hi >> 24, 1);
     if (lane == 0) prev = (x0 > 0) ? (unsigned)__ldg(row + x0 - 1) : 0u;
-    v[0] = (int)prev;
-    v[1] = (int)(lo & 0xff); v[2] = (int)((lo >> 8) & 0xff); v[3] = (int)((lo >> 16) & 0xff); v[4] = (int)(lo >> 24);
-    v[5] = (int)(hi & 0xff); v[6] = (int)((hi >> 8) & 0xff); v[7] = (int)((hi >> 16) & 0xff);
+    v[0] = (int)prev;  // one PRMT per byte
+    v[1] = (int)__byte_perm(lo, 0, 0x4440); v[2] = (int)__byte_perm(lo, 0, 0x4441); v[3] = (int)__byte_perm(lo, 0, 0x4442);
+    v[4] = (int)__byte_perm(lo, 0, 0x4443); v[5] = (int)__byte_perm(hi, 0, 0x4440); v[6] = (int)__byte_perm(hi, 0, 0x4441);
+    v[7] = (int)__byte_perm(hi, 0, 0x4442);
 }
 
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+__device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }  // one REDUX.SUM
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -130,12 +127,11 @@ integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs,
         }
         for (; bb < b; bb++) colc += __ldg(Tp + (size_t)bb * bstride);
     }
-    int off = 0;
-    if (c > 0)
-        for (int idx = tid; idx < b * c; idx += kThreads) {
-            const int bb = idx / c, cc = idx - bb * c;
-            off += __ldg(TT + ((size_t)f * nb + bb) * nc + cc);
-        }
+    int off = 0;  // totals of the tiles above and to the left: warp per band, lane per chunk
+#pragma unroll 1
+    for (int bb = warp; bb < b; bb += 8)
+#pragma unroll 1
+        for (int cc = lane; cc < c; cc += 32) off += __ldg(TT + ((size_t)f * nb + bb) * nc + cc);
     // block reduce `off`, block inclusive scan of `colc`
     off = warp_sum(off);
     int incl = warp_incl_scan(colc, lane);
@@ -156,6 +152,7 @@ integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs,
         int rowbase = 0;
         if (y < P.h) {
             load_shifted<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane, v);
+#pragma unroll 1
             for (int cc = lane; cc < c; cc += 32) rowbase += __ldg(R + ((size_t)f * hpad + y) * nc + cc);
         } else {
 #pragma unroll
@@ -175,12 +172,15 @@ integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs,
     // ---- column scan down the tile, one output column per thread, full-line row stores
     const int X = kChunk * c + tid;
     if (X < P.iw) {
-        int* out = Iout + (size_t)f * P.istride + P.ip /*guard row*/ + X;
+        int* out = Iout + (size_t)f * P.istride + (size_t)(b * kBand + 2) * P.ip /*guard row + zero row*/ + X;
         int run = carry;
         const int rows = min(kBand, P.h - b * kBand);
-        for (int r = 0; r < rows; r++) {
+        const int ipitch = P.ip;
+#pragma unroll 8
+        for (int r = 0; r < rows; r++) {  // running pointer: one 64-bit add per row (the indexed form cost six)
             run += tile[r][tid];
-            out[(size_t)(b * kBand + r + 1) * P.ip] = run;
+            *out = run;
+            out += ipitch;
         }
     }
 }

@@ -135,15 +135,20 @@ nms_scan_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase
     const int i = mb + 2 * yc, j = mb + 2 * xc;
     const int sw = q.sw, sh = q.sh, sp = q.sp, osz = q.osz;
     const float* src = Rbase + (size_t)f * P.rstride + q.resp_off;
+    asm volatile("" : "+l"(src));  // one materialised base pointer: addresses are IMAD.WIDE(index, 4, src)
 
     bool cand_ok = false;
     unsigned packed = 0;
     if (k < ms - 1 && i < sh - mb && j < sw - mb) {
-        const float* c0 = src + (size_t)k * osz + (size_t)i * sp + j;
-        const float* c1 = c0 + osz;
+        // UNSIGNED 32-bit element indices from one materialised base pointer (an octave's layers are < 2^31 elements and
+        // every index is >= 0): an address is IADD + IMAD.WIDE.U32; with size_t products -- or signed ints, which the
+        // compiler widens before adding -- the address arithmetic was half of the kernel's instructions
+        const unsigned usp = sp, uosz = osz;
+        const unsigned u0 = (unsigned)k * uosz + (unsigned)i * usp + (unsigned)j, u1 = u0 + uosz;
         // cell maximum in the reference's scan order, strict > (surfd.cu:699-736)
-        const float v0 = __ldg(c0), v1 = __ldg(c0 + 1), v2 = __ldg(c0 + sp), v3 = __ldg(c0 + sp + 1);
-        const float v4 = __ldg(c1), v5 = __ldg(c1 + 1), v6 = __ldg(c1 + sp), v7 = __ldg(c1 + sp + 1);
+        const float *pa = src + u0, *pb = src + (u0 + usp), *pc = src + u1, *pd = src + (u1 + usp);  // +-1 column: immediate offsets
+        const float v0 = __ldg(pa), v1 = __ldg(pa + 1), v2 = __ldg(pb), v3 = __ldg(pb + 1);
+        const float v4 = __ldg(pc), v5 = __ldg(pc + 1), v6 = __ldg(pd), v7 = __ldg(pd + 1);
         float best = v0;
         int cas = 0;
         if (v1 > best) { best = v1; cas = 1; }
@@ -156,26 +161,34 @@ nms_scan_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase
         bool cnd = !(best < __fmul_rn(P.thresh, 0.8f)) && !(k + 1 == ms - 1 && cas > 3);
         const int s = k + (cas >> 2), r = i + ((cas >> 1) & 1), c = j + (cas & 1);
         if (cnd) {
-            // outward directions: the cell's other member along each axis sits at -d
-            const int ds = (cas & 4) ? 1 : -1, dr = (cas & 2) ? 1 : -1, dc = (cas & 1) ? 1 : -1;
-            const float* ctr = src + (size_t)s * osz + (size_t)r * sp + c;
+            // outward directions: the cell's other member along each axis sits at -d (two's-complement offsets)
+            const unsigned dso = (cas & 4) ? uosz : 0u - uosz, drp = (cas & 2) ? usp : 0u - usp, dc = (cas & 1) ? 1u : ~0u;
+            const unsigned ci = (unsigned)s * uosz + (unsigned)r * usp + (unsigned)c;
             // outer layer s+ds: all nine
-            const float* L = ctr + ds * osz;
-#pragma unroll
-            for (int a = -1; a <= 1; a++)
-#pragma unroll
-                for (int b = -1; b <= 1; b++)
-                    if (best < __ldg(L + a * sp + b)) cnd = false;
+            {
+                const unsigned l1 = ci + dso;
+                const float *q0 = src + (l1 - usp), *q1 = src + l1, *q2 = src + (l1 + usp);
+                if (best < __ldg(q0 - 1)) cnd = false;
+                if (best < __ldg(q0)) cnd = false;
+                if (best < __ldg(q0 + 1)) cnd = false;
+                if (best < __ldg(q1 - 1)) cnd = false;
+                if (best < __ldg(q1)) cnd = false;
+                if (best < __ldg(q1 + 1)) cnd = false;
+                if (best < __ldg(q2 - 1)) cnd = false;
+                if (best < __ldg(q2)) cnd = false;
+                if (best < __ldg(q2 + 1)) cnd = false;
+            }
             // own layer s and inner layer s-ds: the five positions outside the cell's 2x2 footprint
 #pragma unroll
             for (int li = 0; li < 2; li++) {
-                const float* M = ctr - li * ds * osz;
-                const float* rowo = M + dr * sp;  // outward row: three
+                const unsigned m = li ? ci - dso : ci;
+                const float* rowo = src + (m + drp);  // outward row: three
                 if (best < __ldg(rowo - 1)) cnd = false;
                 if (best < __ldg(rowo)) cnd = false;
                 if (best < __ldg(rowo + 1)) cnd = false;
-                if (best < __ldg(M + dc)) cnd = false;            // (r, c+dc)
-                if (best < __ldg(M - dr * sp + dc)) cnd = false;  // (r-dr, c+dc)
+                const unsigned side = m + dc;   // (r, c+dc) and (r-dr, c+dc)
+                if (best < __ldg(src + side)) cnd = false;
+                if (best < __ldg(src + (side - drp))) cnd = false;
             }
         }
         cand_ok = cnd;
