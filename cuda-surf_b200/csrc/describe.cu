@@ -369,21 +369,10 @@ constexpr int kRowTab = 96;
 constexpr int kAhead = 1;  // rows (of one parity) the gathers run ahead of the arithmetic
 constexpr int kRowInvalid = -100;  // 'no current cell row' marker of the sweep
 
-template <int O>
-__device__ __forceinline__ void emit_row(float* __restrict__ h, int lane, int W, int k, int ci, float cfrac1, float cfrac,
-                                         const float (&v)[O]) {
-    if (k < 0 || k >= W) return;
-    if (ci >= 0) {
-        float* e = h + ((k * W + ci) * O) * 32 + lane;
-#pragma unroll
-        for (int b = 0; b < O; b++) e[b * 32] += __fmul_rn(v[b], cfrac1);
-    }
-    if (ci + 1 < W) {
-        float* e = h + ((k * W + ci + 1) * O) * 32 + lane;
-#pragma unroll
-        for (int b = 0; b < O; b++) e[b * 32] += __fmul_rn(v[b], cfrac);
-    }
-}
+// Row stride of the per-warp staging tile T[cell row * O + bin][lane] and of the column-weight table Wc[cell column][lane]:
+// 36 floats = 16-byte aligned rows whose banks advance by 4 per row, so the reduction's LDS.128 of 8 different rows
+// (one per lane group) tile the 32 banks exactly.
+constexpr int kTS = 36;
 
 struct TrueT { static constexpr bool value = true; };
 struct FalseT { static constexpr bool value = false; };
@@ -396,12 +385,16 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     extern __shared__ __align__(16) float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // layout: [4 warps][NF*32] private descriptor copies | [4 warps][kRowTab] row tables | lut2[40]
-    RowEntry* rowT = reinterpret_cast<RowEntry*>(smem + kWarpsPerCta * NF * 32) + warp * kRowTab;
-    float* s_lut2 = smem + kWarpsPerCta * NF * 32 + kWarpsPerCta * kRowTab * 4;
+    // layout: [4 warps][(W*O + W) * kTS] staging tile + column weights | [4 warps][kRowTab] row tables | lut2[40]
+    const int stage = (W * O + W) * kTS;
+    RowEntry* rowT = reinterpret_cast<RowEntry*>(smem + kWarpsPerCta * stage) + warp * kRowTab;
+    float* s_lut2 = smem + kWarpsPerCta * stage + kWarpsPerCta * kRowTab * 4;
     for (int t = threadIdx.x; t < 40; t += blockDim.x) s_lut2[t] = P.lut2[t];
+    // the tile starts finite: lanes without a valid column never write it and enter the reduction with weight 0
+    for (int t = threadIdx.x; t < kWarpsPerCta * stage; t += blockDim.x) smem[t] = 0.f;
     __syncthreads();
-    float* h = smem + warp * NF * 32;
+    float* T = smem + warp * stage;
+    float* Wc = T + W * O * kTS;
     const unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut2);
     const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
     const int ip = P.ip;
@@ -414,7 +407,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
         const float x = pts[pi].x, y = pts[pi].y;
         const KpGeom kg = kp_geom(x, y, pts[pi].scale, W, P.mag_factor, P.doubled);
-        for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};  // descriptor elements lane, lane+32, ... (un-normalised)
         const int step = kg.step, ixc = kg.ixc, iyc = kg.iyc, S = kg.S, R = kg.R;
         const float fx = kg.fx, fy = kg.fy, spacing = kg.spacing;
         const float wofs = __fmaf_rn(fW, 0.5f, -0.5f);
@@ -455,10 +448,11 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
             const float cx = __fadd_rn(cpos, wofs);
             const int c = ixc + j * step;
             const bool colok = jj < side && cx > -1.f && cx < fW && c >= 1 + S && c < P.iw - 1 - S;
+            const int ci = __float2int_rz(cx >= 0.f ? cx : __fsub_rn(cx, 1.f));
+            const float cfrac = __fsub_rn(cx, __int2float_rn(ci)), cfrac1 = __fsub_rn(1.f, cfrac);
             if (colok) {
-                const int ci = __float2int_rz(cx >= 0.f ? cx : __fsub_rn(cx, 1.f));
-                const float cfrac = __fsub_rn(cx, __int2float_rn(ci)), cfrac1 = __fsub_rn(1.f, cfrac);
                 const float cpos2 = __fmul_rn(cpos, cpos);
+                for (int t = 0; t < W * O; t++) T[t * kTS + lane] = 0.f;  // cell rows this lane's sweep never reaches
                 // Column base pointers, made opaque so every gather is ONE IMAD.WIDE (row offset * 4 + base)
                 // instead of a 64-bit add chain per load.
                 const int* pA = I + (c - S);
@@ -470,6 +464,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                 float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
                 float xlo[4] = {0.f, 0.f, 0.f, 0.f}, xhi[4] = {0.f, 0.f, 0.f, 0.f};  // SURF-128: the sums restricted to dy<0 / dx<0
                 auto flush = [&](int k, const float (&sv)[4], const float (&xv)[4]) {
+                    if (k < 0 || k >= W) return;
                     float v[O];
                     if (O == 4) {
                         // bins: dx<0, dx>=0, dy<0, dy>=0 (addUprightSample, surfd.cu:1308)
@@ -480,7 +475,11 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                         v[0] = xv[0]; v[1] = sv[0] - xv[0]; v[2] = xv[1]; v[3] = sv[1] - xv[1];
                         v[4] = xv[2]; v[5] = sv[2] - xv[2]; v[6] = xv[3]; v[7] = sv[3] - xv[3];
                     }
-                    emit_row<O>(h, lane, W, k, ci, cfrac1, cfrac, v);
+                    // staged UNWEIGHTED: the split over the cell columns ci, ci+1 is applied by the reduction below
+                    // (read-modify-write of two private descriptor cells per value was 30-40 % of a pass)
+                    float* t = T + (k * O) * kTS + lane;
+#pragma unroll
+                    for (int b = 0; b < O; b++) t[b * kTS] = v[b];
                 };
                 // The 12 corner values of a sample: rows r-S (m), r (z), r+1 (u), r+S+1 (q); columns c-S (A), c (B),
                 // c+1 (C), c+S+1 (D); m and q need all four columns, z and u only A and D.
@@ -577,20 +576,38 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                     flush(seg, hi, xhi);
                 }
             }
+            // Column weights of this pass (placeInIndex's split over cell columns ci and ci+1, surfd.cu:1199-1271), then
+            // element e = (k*W + cc)*O + o gathers sum_l Wc[cc][l] * T[k*O + o][l] over the 32 lanes' columns.
+            for (int cc = 0; cc < W; cc++)
+                Wc[cc * kTS + lane] = colok ? ((ci == cc ? cfrac1 : 0.f) + (ci + 1 == cc ? cfrac : 0.f)) : 0.f;
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = lane + 32 * u;
+                if (e < NF) {
+                    const int o = e % O, t = e / O;
+                    const int k = (t >= W) + (t >= 2 * W) + (t >= 3 * W), cc = t - k * W;
+                    const float4* tr = reinterpret_cast<const float4*>(T + (k * O + o) * kTS);
+                    const float4* wr = reinterpret_cast<const float4*>(Wc + cc * kTS);
+                    float a = acc[u];
+#pragma unroll
+                    for (int l4 = 0; l4 < 8; l4++) {
+                        const float4 tv = tr[l4], wv = wr[l4];
+                        a = __fmaf_rn(wv.x, tv.x, a); a = __fmaf_rn(wv.y, tv.y, a);
+                        a = __fmaf_rn(wv.z, tv.z, a); a = __fmaf_rn(wv.w, tv.w, a);
+                    }
+                    acc[u] = a;
+                }
+            }
+            __syncwarp();  // the next pass overwrites T and Wc
         }
-        __syncwarp();
-        // reduce the 32 private copies (rotated read: bank == (lane + k) % 32), normalise, store
+        // normalise, store
         float v[4];
         float sq = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            const int e = lane + 32 * u;
-            float acc = 0.f;
-            if (e < NF) {
-                for (int k = 0; k < 32; k++) acc += h[e * 32 + ((lane + k) & 31)];
-            }
-            v[u] = acc;
-            sq = __fmaf_rn(acc, acc, sq);
+            v[u] = acc[u];
+            sq = __fmaf_rn(acc[u], acc[u], sq);
         }
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
@@ -620,7 +637,7 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     const dim3 grid(ctas, nframes), block(kWarpsPerCta * 32);
     if (!P.upright) orient_kernel<<<grid, block, 0, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count);
     if (P.upright) {
-        const size_t smem = ((size_t)kWarpsPerCta * P.nfeatures * 32 + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
+        const size_t smem = ((size_t)kWarpsPerCta * (P.desc_wsz * P.orient_size + P.desc_wsz) * kTS + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
         if (P.orient_size == 4) {
             cudaFuncSetAttribute(describe_upright_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             describe_upright_kernel<4><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
