@@ -101,12 +101,19 @@ __device__ __forceinline__ KpGeom kp_geom(float x, float y, float scale, int W, 
 // q = a / b for 0 <= a < 2^23 with inv = 1.f / b: exact (the +0.5 keeps the product away from the integer boundary)
 __device__ __forceinline__ int div_small(int a, float inv) { return __float2int_rz(__fmul_rn(__int2float_rn(a) + 0.5f, inv)); }
 
+// Column-phase layout of the second integral copy that the gather Hessian reads: within a row, column X sits at
+// (X % 8) * (pitch / 8) + X / 8. Samples of octave o are 2^(o+1) pixels apart, so the 32 lanes of a gather read 4-byte
+// words 8..128 bytes apart in the row-major image (16-32 sectors per request); in this layout the same lanes read
+// consecutive words of one or two planes (4-8 sectors up to octave 2).
+__device__ __forceinline__ int phase_col(int X, int pitch) { return (X & 7) * (pitch >> 3) + (X >> 3); }
+
 // launchers (one translation unit per stage)
 cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_pitch, int w, int h, uint8_t* d_dst,
                               size_t dst_stride, int dst_pitch, int nframes, cudaStream_t st);
 cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
-                            int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);
-cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, float* d_resp, cudaStream_t st);
+                            int* d_integral, int* d_integral_ph, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);
+cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, const int* d_integral_ph, float* d_resp,
+                           cudaStream_t st);
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
                        int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st);
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,

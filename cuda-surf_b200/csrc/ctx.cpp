@@ -51,6 +51,7 @@ struct sb_ctx {
     int next_set = 0;
     // scratch, `batch` frame slots each
     int* d_integral = nullptr;
+    int* d_integral_ph = nullptr;  // second copy, column-phase layout (gather Hessian)
     float* d_resp = nullptr;
     int *d_colsum = nullptr, *d_rowsum = nullptr, *d_tilesum = nullptr;
     int* d_counts = nullptr;
@@ -190,7 +191,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_integral); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
+    cudaFree(ctx->d_integral); cudaFree(ctx->d_integral_ph); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
     cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); 
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     free_match_scratch(ctx->match_ws);
@@ -240,6 +241,7 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     ok(cudaMalloc((void**)&c->d_integral, isz));
+    ok(cudaMalloc((void**)&c->d_integral_ph, isz));
     ok(cudaMalloc((void**)&c->d_resp, rsz));
     ok(cudaMalloc((void**)&c->d_colsum, tsz));
     ok(cudaMalloc((void**)&c->d_rowsum, rowsz));
@@ -260,6 +262,7 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
         // zeroed once: borders of every response layer, row/column 0, padding and guard rows of
         // the integral are never written afterwards
         ok(cudaMemsetAsync(c->d_integral, 0, isz, c->stream));
+        ok(cudaMemsetAsync(c->d_integral_ph, 0, isz, c->stream));
         ok(cudaMemsetAsync(c->d_resp, 0, rsz, c->stream));
         ok(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * B, c->stream));
         ok(cudaMemsetAsync(c->d_cand_count, 0, sizeof(int) * B, c->stream));
@@ -301,6 +304,7 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
                           int slot0 = 0) {
     const PipeP& P = ctx->P;
     int* integral = ctx->d_integral + (size_t)slot0 * P.istride;
+    int* integral_ph = ctx->d_integral_ph + (size_t)slot0 * P.istride;
     float* resp = ctx->d_resp + (size_t)slot0 * P.rstride;
     int* colsum = ctx->d_colsum + (size_t)slot0 * P.nbands * P.nchunks * 256;
     int* rowsum = ctx->d_rowsum + (size_t)slot0 * P.nbands * 32 * P.nchunks;
@@ -314,9 +318,9 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
         CU(launch_upsample2x(d_images, image_stride, pitch, ctx->prm.width, ctx->prm.height, up, ustride, ctx->up_pitch, nframes, st));
         d_images = up; image_stride = ustride; pitch = ctx->up_pitch;
     }
-    CU(launch_integral(P, d_images, image_stride, pitch, nframes, integral, colsum, rowsum, tilesum, st));
+    CU(launch_integral(P, d_images, image_stride, pitch, nframes, integral, integral_ph, colsum, rowsum, tilesum, st));
     if (ev) CU(cudaEventRecord(ev[1], st));
-    CU(launch_hessian(P, nframes, integral, resp, st));
+    CU(launch_hessian(P, nframes, integral, integral_ph, resp, st));
     if (ev) CU(cudaEventRecord(ev[2], st));
     CU(launch_nms(P, nframes, integral, resp, d_points, d_counts, ctx->d_cand + (size_t)slot0 * ctx->cand_cap,
                   ctx->d_cand_count + slot0, ctx->cand_cap, st));

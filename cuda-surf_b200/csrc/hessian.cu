@@ -32,16 +32,36 @@ __device__ __forceinline__ float hessian_det(int dxx, int dyy, int dxy, float no
 // The 32 box corners of a sample lie on 10 rows and 10 columns (same corners as getSum, surfd.cu:334-343):
 //   rows    Dxx: -x3, x3+1 | Dyy: -l-x2, -x2, x2+1, l+x2+1 | Dxy: -x4, 0, 1, x4+1
 //   columns Dxx: -l-x2, -x2, x2+1, l+x2+1 | Dyy: -x3, x3+1 | Dxy: -x4, 0, 1, x4+1
-// ROW(dy) gives a 64-bit row pointer, COL(dx) a 32-bit element offset; the pointers are made opaque so that every
-// gather is ONE IMAD.WIDE (offset * 4 + pointer) + LDG -- written naively the compiler spent 7 integer instructions
-// of 64-bit address arithmetic per load (ncu: 340 instructions per sample, 74 % issue utilisation).
-template <class RowF, class ColF>
-__device__ __forceinline__ float hessian_corners(RowF ROW, ColF COL, int l, float norm) {
+// A thread keeps its lobe and column for all of its samples, so the 10 row offsets (elements) and the 10 column
+// positions -- in the column-phase layout of the second integral copy (common.cuh: phase_col) -- are computed once;
+// a sample then costs 10 row pointers (IMAD.WIDE, made opaque so they are not re-derived per load) and one
+// IMAD.WIDE + LDG per corner. Written naively the compiler spent 7 integer instructions of 64-bit address
+// arithmetic per load (ncu: 340 instructions per sample).
+struct CornerGeom { int roff[10]; int col[10]; };
+
+__device__ __forceinline__ CornerGeom corner_geom(int l, int cx, int ip) {
     const int x2 = l >> 1, x3 = x2 + x2, x4 = x2 + x3;
-    const int* r[10] = {ROW(-x3), ROW(x3 + 1), ROW(-l - x2), ROW(-x2), ROW(x2 + 1), ROW(l + x2 + 1), ROW(-x4), ROW(0), ROW(1), ROW(x4 + 1)};
-    const int c[10] = {COL(-l - x2), COL(-x2), COL(x2 + 1), COL(l + x2 + 1), COL(-x3), COL(x3 + 1), COL(-x4), COL(0), COL(1), COL(x4 + 1)};
+    const int dy[10] = {-x3, x3 + 1, -l - x2, -x2, x2 + 1, l + x2 + 1, -x4, 0, 1, x4 + 1};
+    const int dx[10] = {-l - x2, -x2, x2 + 1, l + x2 + 1, -x3, x3 + 1, -x4, 0, 1, x4 + 1};
+    CornerGeom g;
 #pragma unroll
-    for (int k = 0; k < 10; k++) asm volatile("" : "+l"(r[k]));
+    for (int k = 0; k < 10; k++) { g.roff[k] = dy[k] * ip; g.col[k] = phase_col(cx + dx[k], ip); }
+    return g;
+}
+
+// `row`: the sample's centre row in the column-phase integral copy
+__device__ __forceinline__ float hessian_response(const int* __restrict__ row, const CornerGeom& g, float norm) {
+    const int* r[10];
+    int c[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        // opaque 32-bit offsets: otherwise they are widened once outside the loop and every address is a 64-bit add pair
+        int ro = g.roff[k];
+        c[k] = g.col[k];
+        asm volatile("" : "+r"(ro), "+r"(c[k]));
+        r[k] = row + ro;
+        asm volatile("" : "+l"(r[k]));
+    }
 #define G_(ri, ci) __ldg(r[ri] + c[ci])
     const int wide = G_(1, 3) + G_(0, 0) - G_(0, 3) - G_(1, 0);
     const int midx = G_(1, 2) + G_(0, 1) - G_(0, 2) - G_(1, 1);
@@ -59,20 +79,14 @@ __device__ __forceinline__ float hessian_corners(RowF ROW, ColF COL, int l, floa
     return hessian_det(dxx, dyy, dxy, norm);
 }
 
-// row-major padded integral I (pitch ip)
-__device__ __forceinline__ float hessian_response(const int* __restrict__ I, int ip, int cx, int cy, int l, float norm) {
-    const int* base = I + (size_t)cy * ip + cx;
-    return hessian_corners([&](int dy) { return base + dy * ip; }, [&](int dx) { return dx; }, l, norm);
-}
-
 // grid (tiles * layers, nframes), block 32x8; the layer is the fastest-varying part of blockIdx.x, so the layers of a
 // tile -- and all tiles of a frame -- run while that frame's integral is in L2 (with the layer as blockIdx.z every layer
 // swept all 64 frames again: ncu, 25 MB of DRAM reads per frame for the 8.9 MB integral). A CTA covers 32 x kHessRows outputs of one layer (a thread: kHessRows/8 rows,
 // 8 apart): with a 32x8 tile every CTA pulled its whole 70-pixel filter halo through L2 for 256 outputs (ncu: 94 MB of
 // L2->L1 traffic per frame for the 8.9 MB integral); the taller tile reuses the halo from L1. (Looping the layers inside
 // the CTA as well was 1 % faster in a 64-frame batch and 30 % slower for a single frame.)
-__global__ void __launch_bounds__(256)
-hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int first_tile,
+__global__ void __launch_bounds__(256, 3)
+hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Iphase, float* __restrict__ Rbase, int first_tile,
                int nlayers) {
     const int f = blockIdx.y;
     const int tile = blockIdx.x / nlayers + first_tile;
@@ -84,18 +98,21 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, f
     const int ty = div_small(lt, q.inv_hess_tx), tx = lt - ty * q.hess_tx;
     const int ix = tx * 32 + threadIdx.x;
     if (ix >= q.sw) return;
-    const int* I = Ibase + (size_t)f * P.istride + P.ip;
+    const int* I = Iphase + (size_t)f * P.istride + P.ip;
     float* Rf = Rbase + (size_t)f * P.rstride;
     const int cx = q.delta * ix;
     const int ms = P.max_scale;
     if (i < q.nl) {
         const int b = q.b1[i];
         if (ix < b || ix >= q.sw - b) return;
-#pragma unroll 2
+        const CornerGeom g = corner_geom(q.l[i], cx, P.ip);
+        const float norm = q.norm[i];
+        const int rowstep = q.delta * P.ip;
+#pragma unroll 1
         for (int u = 0; u < kHessRows / 8; u++) {
             const int iy = ty * kHessRows + threadIdx.y + 8 * u;
             if (iy < b || iy >= q.sh - b) continue;
-            const float v = hessian_response(I, P.ip, cx, q.delta * iy, q.l[i], q.norm[i]);
+            const float v = hessian_response(I + (size_t)iy * rowstep, g, norm);
             int s = q.s0 + i;
             Rf[q.resp_off + (size_t)s * q.osz + (size_t)iy * q.sp + ix] = v;
             // write-through of what halfImage would copy into the next octave(s)
@@ -216,7 +233,8 @@ hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
     }
 }
 
-cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, float* d_resp, cudaStream_t st) {
+cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, const int* d_integral_ph, float* d_resp,
+                           cudaStream_t st) {
     const OctaveP& q0 = P.oct[0];
     const bool fast0 = P.sampling == 2 && P.init_lobe == 3 && P.max_scale == 5 && q0.s0 == 0 && q0.nl == 5;
     int first_tile = 0;
@@ -231,7 +249,7 @@ cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, f
             if (P.oct[o].hess_tile0 >= first_tile && P.oct[o].nl > maxnl) maxnl = P.oct[o].nl;
         // (grid.y is the frame: the integral / response slots are indexed by blockIdx.y in every kernel)
         const dim3 grid((P.hess_tiles - first_tile) * maxnl, nframes), block(32, 8);
-        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral, d_resp, first_tile, maxnl);
+        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral_ph, d_resp, first_tile, maxnl);
     }
     return cudaGetLastError();
 }

@@ -104,7 +104,8 @@ integral_reduce(const __grid_constant__ PipeP P, const uint8_t* __restrict__ img
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kThreads)
 integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs, size_t image_stride, int pitch,
-              const int* __restrict__ T, const int* __restrict__ R, const int* __restrict__ TT, int* __restrict__ Iout) {
+              const int* __restrict__ T, const int* __restrict__ R, const int* __restrict__ TT, int* __restrict__ Iout,
+              int* __restrict__ Iph) {
     __shared__ __align__(16) int tile[kBand][kChunk];
     __shared__ int wtot[8];
     __shared__ int s_off;
@@ -176,11 +177,15 @@ integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs,
         int run = carry;
         const int rows = min(kBand, P.h - b * kBand);
         const int ipitch = P.ip;
+        // second copy in the column-phase layout (common.cuh: phase_col) for the gather Hessian: same rows, columns permuted
+        int* outp = Iph + (size_t)f * P.istride + (size_t)(b * kBand + 2) * P.ip + phase_col(X, ipitch);
 #pragma unroll 8
-        for (int r = 0; r < rows; r++) {  // running pointer: one 64-bit add per row (the indexed form cost six)
+        for (int r = 0; r < rows; r++) {  // running pointers: one 64-bit add per row (the indexed form cost six)
             run += tile[r][tid];
             *out = run;
+            *outp = run;
             out += ipitch;
+            outp += ipitch;
         }
     }
 }
@@ -232,15 +237,15 @@ cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_p
 }
 
 cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
-                            int* d_integral, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st) {
+                            int* d_integral, int* d_integral_ph, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st) {
     const dim3 grid(P.nchunks, P.nbands, nframes), block(kThreads);
     const bool aligned = (pitch % 8 == 0) && (image_stride % 8 == 0) && ((uintptr_t)d_images % 8 == 0);
     if (aligned) {
         integral_reduce<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
-        integral_scan<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral);
+        integral_scan<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
     } else {
         integral_reduce<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
-        integral_scan<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral);
+        integral_scan<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
     }
     return cudaGetLastError();
 }
