@@ -85,7 +85,7 @@ __device__ __forceinline__ float hessian_response(const int* __restrict__ row, c
 // 8 apart): with a 32x8 tile every CTA pulled its whole 70-pixel filter halo through L2 for 256 outputs (ncu: 94 MB of
 // L2->L1 traffic per frame for the 8.9 MB integral); the taller tile reuses the halo from L1. (Looping the layers inside
 // the CTA as well was 1 % faster in a 64-frame batch and 30 % slower for a single frame.)
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Iphase, float* __restrict__ Rbase, int first_tile,
                int nlayers) {
     const int f = blockIdx.y;

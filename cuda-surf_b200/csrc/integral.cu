@@ -21,26 +21,42 @@ constexpr int kBand = 32;     // rows per tile
 constexpr int kChunk = 256;   // output columns per tile
 constexpr int kThreads = 256;
 
-// 8 pixels for output columns X = 256c + 8*lane + k  (image column X-1), zero outside the image.
+// 8 pixels for output columns X = 256c + 8*lane + k  (image column X-1), zero outside the image: the raw load (8 bytes of
+// this lane's aligned group + lane 0's byte from the previous chunk) and the unpack are separate, so a kernel can issue
+// the loads of several rows before it waits for any of them.
+struct RawRow { unsigned lo, hi, prev0; };
+
 template <bool ALIGNED>
-__device__ __forceinline__ void load_shifted(const uint8_t* __restrict__ row, int w, int c, int lane, int (&v)[8]) {
+__device__ __forceinline__ RawRow load_raw(const uint8_t* __restrict__ row, int w, int c, int lane) {
     const int x0 = kChunk * c + 8 * lane;  // first image column of this lane's aligned 8-byte group
-    unsigned lo = 0, hi = 0;
+    RawRow q;
+    q.lo = 0; q.hi = 0;
     if (ALIGNED && x0 + 7 < w) {
         const uint2 a = __ldg(reinterpret_cast<const uint2*>(row + x0));
-        lo = a.x; hi = a.y;
+        q.lo = a.x; q.hi = a.y;
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (x0 + k < w) lo |= (unsigned)__ldg(row + x0 + k) << (8 * k);
+        for (int k = 0; k < 4; k++) if (x0 + k < w) q.lo |= (unsigned)__ldg(row + x0 + k) << (8 * k);
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (x0 + 4 + k < w) hi |= (unsigned)__ldg(row + x0 + 4 + k) << (8 * k);
+        for (int k = 0; k < 4; k++) if (x0 + 4 + k < w) q.hi |= (unsigned)__ldg(row + x0 + 4 + k) << (8 * k);
     }
-    unsigned prev = __shfl_up_sync(0xffffffffu, hi >> 24, 1);
-    if (lane == 0) prev = (x0 > 0) ? (unsigned)__ldg(row + x0 - 1) : 0u;
+    q.prev0 = (lane == 0 && x0 > 0) ? (unsigned)__ldg(row + x0 - 1) : 0u;
+    return q;
+}
+
+__device__ __forceinline__ void unpack_shifted(const RawRow& q, int lane, int (&v)[8]) {
+    unsigned prev = __shfl_up_sync(0xffffffffu, q.hi >> 24, 1);
+    if (lane == 0) prev = q.prev0;
+    const unsigned lo = q.lo, hi = q.hi;
     v[0] = (int)prev;  // one PRMT per byte
     v[1] = (int)__byte_perm(lo, 0, 0x4440); v[2] = (int)__byte_perm(lo, 0, 0x4441); v[3] = (int)__byte_perm(lo, 0, 0x4442);
     v[4] = (int)__byte_perm(lo, 0, 0x4443); v[5] = (int)__byte_perm(hi, 0, 0x4440); v[6] = (int)__byte_perm(hi, 0, 0x4441);
     v[7] = (int)__byte_perm(hi, 0, 0x4442);
+}
+
+template <bool ALIGNED>
+__device__ __forceinline__ void load_shifted(const uint8_t* __restrict__ row, int w, int c, int lane, int (&v)[8]) {
+    unpack_shifted(load_raw<ALIGNED>(row, w, c, lane), lane, v);
 }
 
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }  // one REDUX.SUM
@@ -101,21 +117,36 @@ integral_reduce(const __grid_constant__ PipeP P, const uint8_t* __restrict__ img
 }
 
 // Pass B. grid (nchunks, nbands, nframes), 256 threads, 32 KB static shared memory.
+// Columns first, rows last: the tile's pixels are summed DOWN the columns (starting from the column sums of the bands
+// above), then every row is prefix-summed ALONG x by one warp with 8 consecutive output columns per lane. The values a
+// lane ends with are final, so it stores them twice without any scatter: two 128-bit stores into the row-major image and,
+// for k = 0..7, one word into plane k of the column-phase copy (common.cuh: phase_col) -- lane-consecutive, one full
+// 128-byte line per plane. (With the column scan last, a warp held 32 consecutive columns of one row and the phase copy
+// cost 8 store wavefronts per instruction: +2 us per 1080p frame.)
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kThreads)
 integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs, size_t image_stride, int pitch,
               const int* __restrict__ T, const int* __restrict__ R, const int* __restrict__ TT, int* __restrict__ Iout,
               int* __restrict__ Iph) {
     __shared__ __align__(16) int tile[kBand][kChunk];
-    __shared__ int wtot[8];
-    __shared__ int s_off;
+    __shared__ int s_rowbase[kBand];
+    __shared__ int s_offw[8];
     const int c = blockIdx.x, b = blockIdx.y, f = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nb = P.nbands, nc = P.nchunks;
     const uint8_t* img = imgs + (size_t)f * image_stride;
     const int hpad = nb * kBand;
 
-    // ---- carry row: integral at the top edge of this band, for this thread's output column
+    // Every global load of the tile is issued before the first use (one exposed memory latency per CTA, two barriers):
+    // ---- raw pixels: warp per row, rows warp, warp+8, warp+16, warp+24
+    RawRow raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int y = b * kBand + warp + 8 * u;
+        if (y < P.h) raw[u] = load_raw<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane);
+        else { raw[u].lo = 0; raw[u].hi = 0; raw[u].prev0 = 0; }
+    }
+    // ---- column carry: sum of this output column over the bands above
     int colc = 0;
     {
         const int* Tp = T + (((size_t)f * nb) * nc + c) * kChunk + tid;
@@ -128,64 +159,75 @@ integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs,
         }
         for (; bb < b; bb++) colc += __ldg(Tp + (size_t)bb * bstride);
     }
-    int off = 0;  // totals of the tiles above and to the left: warp per band, lane per chunk
+    // ---- totals of the tiles above and to the left: warp per band, lane per chunk
+    int off = 0;
 #pragma unroll 1
     for (int bb = warp; bb < b; bb += 8)
 #pragma unroll 1
         for (int cc = lane; cc < c; cc += 32) off += __ldg(TT + ((size_t)f * nb + bb) * nc + cc);
-    // block reduce `off`, block inclusive scan of `colc`
-    off = warp_sum(off);
-    int incl = warp_incl_scan(colc, lane);
-    if (lane == 31) wtot[warp] = incl;
-    if (tid == 0) s_off = 0;
-    __syncthreads();
-    if (lane == 0 && off != 0) atomicAdd(&s_off, off);
-    int wbase = 0;
-#pragma unroll
-    for (int wq = 0; wq < 8; wq++) if (wq < warp) wbase += wtot[wq];
-    __syncthreads();
-    const int carry = s_off + wbase + incl;
-
-    // ---- row scans: warp per row, 8 pixels per lane
-    for (int r = warp; r < kBand; r += 8) {
-        const int y = b * kBand + r;
-        int v[8];
-        int rowbase = 0;
-        if (y < P.h) {
-            load_shifted<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane, v);
+    // ---- row sums of the chunks to the left (warp 0, lane = row of the band)
+    int rleft = 0;
+    if (warp == 0) {
+        const int* Rp = R + ((size_t)f * hpad + b * kBand + lane) * nc;
 #pragma unroll 1
-            for (int cc = lane; cc < c; cc += 32) rowbase += __ldg(R + ((size_t)f * hpad + y) * nc + cc);
-        } else {
+        for (int cc = 0; cc < c; cc++) rleft += __ldg(Rp + cc);
+    }
+    off = warp_sum(off);
+    if (lane == 0) s_offw[warp] = off;
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = 0;
+    for (int u = 0; u < 4; u++) {
+        int v[8];
+        unpack_shifted(raw[u], lane, v);
+        int4* dst = reinterpret_cast<int4*>(&tile[warp + 8 * u][8 * lane]);
+        dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+    // ---- row bases: integral just left of this chunk at every row of the band = tiles above-left + the chunks' row sums
+    // down to that row
+    if (warp == 0) {
+        int o = 0;
+#pragma unroll
+        for (int wq = 0; wq < 8; wq++) o += s_offw[wq];
+        s_rowbase[lane] = o + warp_incl_scan(rleft, lane);
+    }
+    // ---- column sums down the tile, one output column per thread
+    {
+        int run = colc;
+#pragma unroll 8
+        for (int r = 0; r < kBand; r++) {
+            run += tile[r][tid];
+            tile[r][tid] = run;
         }
-        rowbase = warp_sum(rowbase);
-#pragma unroll
-        for (int k = 1; k < 8; k++) v[k] += v[k - 1];
-        const int inc = warp_incl_scan(v[7], lane);
-        const int base = rowbase + inc - v[7];
-        int4* dst = reinterpret_cast<int4*>(&tile[r][8 * lane]);
-        dst[0] = make_int4(base + v[0], base + v[1], base + v[2], base + v[3]);
-        dst[1] = make_int4(base + v[4], base + v[5], base + v[6], base + v[7]);
     }
     __syncthreads();
 
-    // ---- column scan down the tile, one output column per thread, full-line row stores
-    const int X = kChunk * c + tid;
-    if (X < P.iw) {
-        int* out = Iout + (size_t)f * P.istride + (size_t)(b * kBand + 2) * P.ip /*guard row + zero row*/ + X;
-        int run = carry;
-        const int rows = min(kBand, P.h - b * kBand);
-        const int ipitch = P.ip;
-        // second copy in the column-phase layout (common.cuh: phase_col) for the gather Hessian: same rows, columns permuted
-        int* outp = Iph + (size_t)f * P.istride + (size_t)(b * kBand + 2) * P.ip + phase_col(X, ipitch);
-#pragma unroll 8
-        for (int r = 0; r < rows; r++) {  // running pointers: one 64-bit add per row (the indexed form cost six)
-            run += tile[r][tid];
-            *out = run;
-            *outp = run;
-            out += ipitch;
-            outp += ipitch;
+    // ---- row scans and stores: warp per row
+    const int rows = min(kBand, P.h - b * kBand);
+    const int X0 = kChunk * c + 8 * lane;
+    const int ipitch = P.ip, pw = ipitch >> 3;
+    for (int r = warp; r < rows; r += 8) {
+        const int4* src = reinterpret_cast<const int4*>(&tile[r][8 * lane]);
+        const int4 lo = src[0], hi = src[1];
+        int v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int k = 1; k < 8; k++) v[k] += v[k - 1];
+        const int inc = warp_incl_scan(v[7], lane);
+        const int base = s_rowbase[r] + inc - v[7];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] += base;
+        const size_t rowoff = (size_t)f * P.istride + (size_t)(b * kBand + r + 2) * ipitch;  // guard row + zero row
+        int* out = Iout + rowoff + X0;
+        int* outp = Iph + rowoff + (X0 >> 3);
+        if (X0 + 7 < P.iw) {
+            reinterpret_cast<int4*>(out)[0] = make_int4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<int4*>(out)[1] = make_int4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int k = 0; k < 8; k++) outp[k * pw] = v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (X0 + k < P.iw) { out[k] = v[k]; outp[k * pw] = v[k]; }
         }
     }
 }
