@@ -207,6 +207,136 @@ nms_scan_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase
     }
 }
 
+// The same scan for the standard 5-layer octave (max_scale 5: cell layers z = 0, 1 <-> k = 1, 3), staged through shared
+// memory. The per-cell kernel above makes two dependent trips to memory (the cell's 8 values, then -- for the warps that
+// hold a candidate, i.e. most of them -- its 19 neighbours) and reads every layer from two z-slices; ncu showed it
+// latency-bound (long scoreboard 11 per issue, 36 % of DRAM peak). Here a CTA loads the 5 layers under its 32x8 cells
+// (18+dm rows x 66+dm columns, dm = offset between the two cell lattices) once, all loads in flight together, and both
+// z-slices are decided from shared memory. grid (sum over octaves of nms_tx*nms_ty, nframes), block 32x8.
+constexpr int kNmsR = 20, kNmsC = 72;  // staged rows / padded columns: dm <= 2
+
+__global__ void __launch_bounds__(256)
+nms_scan_tile_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase, unsigned* __restrict__ cand,
+                     int* __restrict__ cand_count, int cand_cap) {
+    __shared__ float blk[5][kNmsR][kNmsC];
+    const int f = blockIdx.y;
+    int lt = blockIdx.x, o = 0;
+    while (o + 1 < P.noctaves && lt >= P.oct[o].nms_tx * P.oct[o].nms_ty) { lt -= P.oct[o].nms_tx * P.oct[o].nms_ty; o++; }
+    const OctaveP& q = P.oct[o];
+    const int ty = div_small(lt, q.inv_nms_tx), tx = lt - ty * q.nms_tx;
+    const int mlo = min(q.mb[0], q.mb[1]), dm = max(q.mb[0], q.mb[1]) - mlo;
+    const int row0 = mlo + 16 * ty - 1, col0 = mlo + 64 * tx - 1;
+    const int NR = 18 + dm, NC = 66 + dm;
+    const int sw = q.sw, sh = q.sh;
+    const unsigned usp = q.sp, uosz = q.osz;
+    const float* src = Rbase + (size_t)f * P.rstride + q.resp_off;
+    asm volatile("" : "+l"(src));
+    const int lane = threadIdx.x, ly = threadIdx.y, tid = ly * 32 + lane;
+    {
+        const float inv_nc = 1.f / (float)NC;
+        const int n = NR * NC;  // <= 20 * 68: at most 6 positions per thread, staged in two groups of three so that 15 loads
+        // are in flight per thread before the first shared-memory store waits on one (a plain loop serialised a memory
+        // round trip per position)
+        float* flat = &blk[0][0][0];
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            float v[3][5];
+            int si[3];
+#pragma unroll
+            for (int it = 0; it < 3; it++) {
+                const int e = tid + 256 * (3 * g + it);
+                const int r = div_small(e, inv_nc), c = e - r * NC;
+                const int gr = row0 + r, gc = col0 + c;
+                si[it] = e < n ? r * kNmsC + c : -1;
+                const bool in = e < n && gr < sh && gc < sw;
+                const unsigned gi = (unsigned)gr * usp + (unsigned)gc;
+#pragma unroll
+                for (int s = 0; s < 5; s++) v[it][s] = in ? __ldg(src + (gi + (unsigned)s * uosz)) : 0.f;
+            }
+#pragma unroll
+            for (int it = 0; it < 3; it++)
+                if (si[it] >= 0) {
+#pragma unroll
+                    for (int s = 0; s < 5; s++) flat[s * (kNmsR * kNmsC) + si[it]] = v[it][s];
+                }
+        }
+    }
+    __syncthreads();
+
+    const int ms = P.max_scale;
+    constexpr int LS = kNmsR * kNmsC;  // layer stride in the staged block
+    bool okz[2] = {false, false};
+    unsigned pkz[2] = {0u, 0u};
+#pragma unroll
+    for (int z = 0; z < 2; z++) {
+        const int k = 2 * z + 1;
+        const int mb = q.mb[z];
+        const int i = mb + 2 * (8 * ty + ly), j = mb + 2 * (32 * tx + lane);
+        if (i < sh - mb && j < sw - mb) {
+            const float* c0 = &blk[k][i - row0][j - col0];
+            const float* c1 = c0 + LS;
+            // cell maximum in the reference's scan order, strict > (surfd.cu:699-736)
+            const float v0 = c0[0], v1 = c0[1], v2 = c0[kNmsC], v3 = c0[kNmsC + 1];
+            const float v4 = c1[0], v5 = c1[1], v6 = c1[kNmsC], v7 = c1[kNmsC + 1];
+            float best = v0;
+            int cas = 0;
+            if (v1 > best) { best = v1; cas = 1; }
+            if (v2 > best) { best = v2; cas = 2; }
+            if (v3 > best) { best = v3; cas = 3; }
+            if (v4 > best) { best = v4; cas = 4; }
+            if (v5 > best) { best = v5; cas = 5; }
+            if (v6 > best) { best = v6; cas = 6; }
+            if (v7 > best) { best = v7; cas = 7; }
+            bool cnd = !(best < __fmul_rn(P.thresh, 0.8f)) && !(k + 1 == ms - 1 && cas > 3);
+            const int s = k + (cas >> 2), r = i + ((cas >> 1) & 1), c = j + (cas & 1);
+            if (cnd) {
+                // outward directions: the cell's other member along each axis sits at -d
+                const int dso = (cas & 4) ? LS : -LS, drp = (cas & 2) ? kNmsC : -kNmsC, dc = (cas & 1) ? 1 : -1;
+                const float* ctr = &blk[s][r - row0][c - col0];
+                const float* q1 = ctr + dso;  // outer layer s+ds: all nine
+                if (best < q1[-kNmsC - 1]) cnd = false;
+                if (best < q1[-kNmsC]) cnd = false;
+                if (best < q1[-kNmsC + 1]) cnd = false;
+                if (best < q1[-1]) cnd = false;
+                if (best < q1[0]) cnd = false;
+                if (best < q1[1]) cnd = false;
+                if (best < q1[kNmsC - 1]) cnd = false;
+                if (best < q1[kNmsC]) cnd = false;
+                if (best < q1[kNmsC + 1]) cnd = false;
+                // own layer s and inner layer s-ds: the five positions outside the cell's 2x2 footprint
+#pragma unroll
+                for (int li = 0; li < 2; li++) {
+                    const float* m = li ? ctr - dso : ctr;
+                    const float* rowo = m + drp;  // outward row: three
+                    if (best < rowo[-1]) cnd = false;
+                    if (best < rowo[0]) cnd = false;
+                    if (best < rowo[1]) cnd = false;
+                    if (best < m[dc]) cnd = false;        // (r, c+dc)
+                    if (best < m[dc - drp]) cnd = false;  // (r-dr, c+dc)
+                }
+            }
+            okz[z] = cnd;
+            pkz[z] = (unsigned)c | ((unsigned)r << 13) | ((unsigned)s << kCandShiftS) | ((unsigned)o << kCandShiftO);
+        }
+    }
+    const unsigned m0 = __ballot_sync(0xffffffffu, okz[0]), m1 = __ballot_sync(0xffffffffu, okz[1]);
+    if (m0 | m1) {
+        const int n0 = __popc(m0);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&cand_count[f], n0 + __popc(m1));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned below = (1u << lane) - 1u;
+        if (okz[0]) {
+            const int slot = base + __popc(m0 & below);
+            if (slot < cand_cap) cand[(size_t)f * cand_cap + slot] = pkz[0];
+        }
+        if (okz[1]) {
+            const int slot = base + n0 + __popc(m1 & below);
+            if (slot < cand_cap) cand[(size_t)f * cand_cap + slot] = pkz[1];
+        }
+    }
+}
+
 // grid (ctas, nframes), 128 threads, grid-stride over the frame's candidates.
 __global__ void __launch_bounds__(128)
 nms_refine_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const float* __restrict__ Rbase,
@@ -296,7 +426,18 @@ __global__ void clamp_counts_kernel(int* counts, int n, int max_pts, int* cand_c
 
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
                        int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st) {
-    nms_scan_kernel<<<dim3(P.nms_tiles, nframes), dim3(32, 8), 0, st>>>(P, d_resp, d_cand, d_cand_count, cand_cap);
+    // standard octaves (5 layers, the two cell lattices at most 2 samples apart): shared-memory scan, one CTA per tile
+    bool tiled = P.max_scale == 5;
+    int ctiles = 0;
+    for (int o = 0; o < P.noctaves; o++) {
+        const OctaveP& q = P.oct[o];
+        if (q.nmb != 2 || abs(q.mb[0] - q.mb[1]) > 2) tiled = false;
+        ctiles += q.nms_tx * q.nms_ty;
+    }
+    if (tiled)
+        nms_scan_tile_kernel<<<dim3(ctiles, nframes), dim3(32, 8), 0, st>>>(P, d_resp, d_cand, d_cand_count, cand_cap);
+    else
+        nms_scan_kernel<<<dim3(P.nms_tiles, nframes), dim3(32, 8), 0, st>>>(P, d_resp, d_cand, d_cand_count, cand_cap);
     // ~5 k candidates per 1080p frame: 48 CTAs of 128 threads cover them in one pass, more are looped over
     nms_refine_kernel<<<dim3(48, nframes), 128, 0, st>>>(P, d_integral, d_resp, d_cand, d_cand_count, cand_cap, d_points, d_counts);
     return cudaGetLastError();
