@@ -89,11 +89,14 @@ __global__ void __launch_bounds__(256, 4)
 hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Iphase, float* __restrict__ Rbase, int first_tile,
                int nlayers) {
     const int f = blockIdx.y;
-    const int tile = blockIdx.x / nlayers + first_tile;
-    const int i = blockIdx.x - (blockIdx.x / nlayers) * nlayers;  // the computed layer
+    // nlayers > 0: one CTA per (tile, layer), the layer fastest; nlayers == 0: one CTA per tile loops over its layers, which
+    // share the tile's patch of the integral in L1 (used for batches, where there are CTAs enough without the split)
+    const int tile = (nlayers > 0 ? blockIdx.x / nlayers : blockIdx.x) + first_tile;
     int o = 0;
     while (o + 1 < P.noctaves && tile >= P.oct[o + 1].hess_tile0) o++;
     const OctaveP& q = P.oct[o];
+    const int i0 = nlayers > 0 ? blockIdx.x - (blockIdx.x / nlayers) * nlayers : 0;
+    const int i1 = nlayers > 0 ? min(i0 + 1, q.nl) : q.nl;
     const int lt = tile - q.hess_tile0;
     const int ty = div_small(lt, q.inv_hess_tx), tx = lt - ty * q.hess_tx;
     const int ix = tx * 32 + threadIdx.x;
@@ -102,9 +105,10 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Iphase, 
     float* Rf = Rbase + (size_t)f * P.rstride;
     const int cx = q.delta * ix;
     const int ms = P.max_scale;
-    if (i < q.nl) {
+#pragma unroll 1
+    for (int i = i0; i < i1; i++) {
         const int b = q.b1[i];
-        if (ix < b || ix >= q.sw - b) return;
+        if (ix < b || ix >= q.sw - b) continue;
         const CornerGeom g = corner_geom(q.l[i], cx, P.ip);
         const float norm = q.norm[i];
         const int rowstep = q.delta * P.ip;
@@ -248,8 +252,9 @@ cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, c
         for (int o = 0; o < P.noctaves; o++)
             if (P.oct[o].hess_tile0 >= first_tile && P.oct[o].nl > maxnl) maxnl = P.oct[o].nl;
         // (grid.y is the frame: the integral / response slots are indexed by blockIdx.y in every kernel)
-        const dim3 grid((P.hess_tiles - first_tile) * maxnl, nframes), block(32, 8);
-        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral_ph, d_resp, first_tile, maxnl);
+        const bool fuse = nframes >= 16;
+        const dim3 grid((P.hess_tiles - first_tile) * (fuse ? 1 : maxnl), nframes), block(32, 8);
+        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral_ph, d_resp, first_tile, fuse ? 0 : maxnl);
     }
     return cudaGetLastError();
 }
