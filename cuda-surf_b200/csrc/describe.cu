@@ -467,9 +467,9 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                     if (k < 0 || k >= W) return;
                     float v[O];
                     if (O == 4) {
-                        // bins: dx<0, dx>=0, dy<0, dy>=0 (addUprightSample, surfd.cu:1308)
-                        v[0] = 0.5f * (sv[0] - sv[1]); v[1] = 0.5f * (sv[0] + sv[1]);
-                        v[2] = 0.5f * (sv[2] - sv[3]); v[3] = 0.5f * (sv[2] + sv[3]);
+                        // staged as signed sum / sum of magnitudes; the split by sign (addUprightSample, surfd.cu:1308:
+                        // bins dx<0, dx>=0, dy<0, dy>=0 = (S -/+ A)/2) is linear and applied once, after the reduction
+                        v[0] = sv[0]; v[1] = sv[1]; v[2] = sv[2]; v[3] = sv[3];
                     } else {
                         // SURF-128 (surfd.cu:1312-1313): dx,|dx| split by sign of dy; dy,|dy| split by sign of dx
                         v[0] = xv[0]; v[1] = sv[0] - xv[0]; v[2] = xv[1]; v[3] = sv[1] - xv[1];
@@ -601,13 +601,19 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
             }
             __syncwarp();  // the next pass overwrites T and Wc
         }
-        // normalise, store
+        // split by sign (O == 4: elements o = 0,1 hold S, A of dx and become (S-A)/2, (S+A)/2; o = 2,3 likewise for dy: the
+        // partner is the neighbouring lane), normalise, store
         float v[4];
         float sq = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            v[u] = acc[u];
-            sq = __fmaf_rn(acc[u], acc[u], sq);
+            float a = acc[u];
+            if (O == 4) {
+                const float pr = __shfl_xor_sync(0xffffffffu, a, 1);
+                a = (lane & 1) ? 0.5f * (pr + a) : 0.5f * (a - pr);
+            }
+            v[u] = a;
+            sq = __fmaf_rn(a, a, sq);
         }
 #pragma unroll
         for (int o2 = 16; o2 > 0; o2 >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o2);
