@@ -124,7 +124,7 @@ integral_reduce(const __grid_constant__ PipeP P, const uint8_t* __restrict__ img
 // 128-byte line per plane. (With the column scan last, a warp held 32 consecutive columns of one row and the phase copy
 // cost 8 store wavefronts per instruction: +2 us per 1080p frame.)
 template <bool ALIGNED>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs, size_t image_stride, int pitch,
               const int* __restrict__ T, const int* __restrict__ R, const int* __restrict__ TT, int* __restrict__ Iout,
               int* __restrict__ Iph) {
@@ -146,31 +146,47 @@ integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs,
         if (y < P.h) raw[u] = load_raw<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane);
         else { raw[u].lo = 0; raw[u].hi = 0; raw[u].prev0 = 0; }
     }
+    // The three look-backs below are sums of independent loads; each is written as groups of predicated loads so that a
+    // group is ONE exposed memory latency (as plain loops with a running sum, every iteration waited for its load: up to
+    // 8 + 5 + 7 serial round trips per CTA at 1080p).
     // ---- column carry: sum of this output column over the bands above
     int colc = 0;
     {
         const int* Tp = T + (((size_t)f * nb) * nc + c) * kChunk + tid;
         const size_t bstride = (size_t)nc * kChunk;
-        int bb = 0;
-        for (; bb + 4 <= b; bb += 4) {
-            const int a0 = __ldg(Tp + (size_t)bb * bstride), a1 = __ldg(Tp + (size_t)(bb + 1) * bstride);
-            const int a2 = __ldg(Tp + (size_t)(bb + 2) * bstride), a3 = __ldg(Tp + (size_t)(bb + 3) * bstride);
-            colc += (a0 + a1) + (a2 + a3);
+#pragma unroll 1
+        for (int b0 = 0; b0 < b; b0 += 16) {
+            int a[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) a[k] = (b0 + k < b) ? __ldg(Tp + (size_t)(b0 + k) * bstride) : 0;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) colc += (a[k] + a[k + 1]) + (a[k + 2] + a[k + 3]);
         }
-        for (; bb < b; bb++) colc += __ldg(Tp + (size_t)bb * bstride);
     }
-    // ---- totals of the tiles above and to the left: warp per band, lane per chunk
+    // ---- totals of the tiles above and to the left: warp per band (4 bands in flight), lane per chunk
     int off = 0;
 #pragma unroll 1
-    for (int bb = warp; bb < b; bb += 8)
-#pragma unroll 1
-        for (int cc = lane; cc < c; cc += 32) off += __ldg(TT + ((size_t)f * nb + bb) * nc + cc);
-    // ---- row sums of the chunks to the left (warp 0, lane = row of the band)
+    for (int bb = warp; bb < b; bb += 32) {
+        int a[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            a[k] = 0;
+            if (bb + 8 * k < b)
+                for (int cc = lane; cc < c; cc += 32) a[k] += __ldg(TT + ((size_t)f * nb + bb + 8 * k) * nc + cc);
+        }
+        off += (a[0] + a[1]) + (a[2] + a[3]);
+    }
+    // ---- row sums of the chunks to the left (warp 0, lane = row of the band), 8 chunks in flight
     int rleft = 0;
     if (warp == 0) {
         const int* Rp = R + ((size_t)f * hpad + b * kBand + lane) * nc;
 #pragma unroll 1
-        for (int cc = 0; cc < c; cc++) rleft += __ldg(Rp + cc);
+        for (int c0 = 0; c0 < c; c0 += 8) {
+            int a[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[k] = (c0 + k < c) ? __ldg(Rp + c0 + k) : 0;
+            rleft += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        }
     }
     off = warp_sum(off);
     if (lane == 0) s_offw[warp] = off;
