@@ -151,10 +151,13 @@ constexpr int kPW = 96, kPH = 64;            // staged patch (integral elements)
 constexpr int kQW = kPW / 2, kQH = kPH / 2;  // plane dims
 constexpr int kPlane = kQW * kQH;            // 1536 words
 constexpr int kHalo = 16;                    // patch origin = 2*tile origin - kHalo
+// the two planes of odd patch rows start 16 words later: a staging warp covers the end of one patch row and the start of
+// the next (24 int4 per row), whose 64-bit stores otherwise meet in banks 0..15 (ncu: 7 % of the wavefronts were conflicts)
+constexpr int kRowPar = 2 * kPlane + 16;
 
 // word offset of patch element (cy + dy, cx + dx) relative to the thread base (ly*kQW + lx)
 __host__ __device__ constexpr int corner_off(int dx, int dy) {
-    return (((dy + kHalo) & 1) * 2 + ((dx + kHalo) & 1)) * kPlane + ((dy + kHalo) >> 1) * kQW + ((dx + kHalo) >> 1);
+    return ((dy + kHalo) & 1) * kRowPar + ((dx + kHalo) & 1) * kPlane + ((dy + kHalo) >> 1) * kQW + ((dx + kHalo) >> 1);
 }
 
 // ctr = the four corners (0,0), (1,0), (0,1), (1,1) [as (dx,dy)] around the sample: every layer's Dxy uses them, so
@@ -204,7 +207,7 @@ __device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict
 // grid (tiles_x * tiles_y, nframes), 256 threads, 24 KB static shared memory
 __global__ void __launch_bounds__(256)
 hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int tiles_x) {
-    __shared__ __align__(16) int patch[4 * kPlane];
+    __shared__ __align__(16) int patch[4 * kPlane + 16];
     const int f = blockIdx.y;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int* I = Ibase + (size_t)f * P.istride + P.ip;
@@ -215,7 +218,7 @@ hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
         const int y = Y0 + row, x = X0 + 4 * k;
         int4 v = make_int4(0, 0, 0, 0);
         if (y >= 0 && y < P.ih && x >= 0 && x + 3 < P.ip) v = __ldg(reinterpret_cast<const int4*>(I + (size_t)y * P.ip + x));
-        int* dst = patch + ((row & 1) * 2) * kPlane + (row >> 1) * kQW + 2 * k;
+        int* dst = patch + (row & 1) * kRowPar + (row >> 1) * kQW + 2 * k;
         *reinterpret_cast<int2*>(dst) = make_int2(v.x, v.z);
         *reinterpret_cast<int2*>(dst + kPlane) = make_int2(v.y, v.w);
     }
