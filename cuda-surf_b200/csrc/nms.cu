@@ -215,51 +215,47 @@ nms_scan_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase
 // z-slices are decided from shared memory. grid (sum over octaves of nms_tx*nms_ty, nframes), block 32x8.
 constexpr int kNmsR = 20, kNmsC = 72;  // staged rows / padded columns: dm <= 2
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 nms_scan_tile_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase, unsigned* __restrict__ cand,
                      int* __restrict__ cand_count, int cand_cap) {
-    __shared__ float blk[5][kNmsR][kNmsC];
+    __shared__ __align__(16) float blk[5][kNmsR][kNmsC];
     const int f = blockIdx.y;
     int lt = blockIdx.x, o = 0;
     while (o + 1 < P.noctaves && lt >= P.oct[o].nms_tx * P.oct[o].nms_ty) { lt -= P.oct[o].nms_tx * P.oct[o].nms_ty; o++; }
     const OctaveP& q = P.oct[o];
     const int ty = div_small(lt, q.inv_nms_tx), tx = lt - ty * q.nms_tx;
     const int mlo = min(q.mb[0], q.mb[1]), dm = max(q.mb[0], q.mb[1]) - mlo;
-    const int row0 = mlo + 16 * ty - 1, col0 = mlo + 64 * tx - 1;
-    const int NR = 18 + dm, NC = 66 + dm;
+    // staged block: rows row0 .. row0+NR-1, columns from col0 rounded down to a multiple of 4 (128-bit loads; the response
+    // rows are 128-byte aligned and zero beyond their width), 72 columns = 66 + dm + the rounding
+    const int row0 = mlo + 16 * ty - 1, col0 = (mlo + 64 * tx - 1) & ~3;
+    const int NR = 18 + dm;
     const int sw = q.sw, sh = q.sh;
     const unsigned usp = q.sp, uosz = q.osz;
     const float* src = Rbase + (size_t)f * P.rstride + q.resp_off;
     asm volatile("" : "+l"(src));
     const int lane = threadIdx.x, ly = threadIdx.y, tid = ly * 32 + lane;
     {
-        const float inv_nc = 1.f / (float)NC;
-        const int n = NR * NC;  // <= 20 * 68: at most 6 positions per thread, staged in two groups of three so that 15 loads
-        // are in flight per thread before the first shared-memory store waits on one (a plain loop serialised a memory
-        // round trip per position)
-        float* flat = &blk[0][0][0];
+        // 5 layers x 20 rows x 18 float4 = 1800 positions, 8 per thread, all 8 x 128-bit loads in flight before the first
+        // shared-memory store waits on one
+        float4* flat = reinterpret_cast<float4*>(&blk[0][0][0]);
+        float4 v[8];
+        int si[8];
 #pragma unroll
-        for (int g = 0; g < 2; g++) {
-            float v[3][5];
-            int si[3];
-#pragma unroll
-            for (int it = 0; it < 3; it++) {
-                const int e = tid + 256 * (3 * g + it);
-                const int r = div_small(e, inv_nc), c = e - r * NC;
-                const int gr = row0 + r, gc = col0 + c;
-                si[it] = e < n ? r * kNmsC + c : -1;
-                const bool in = e < n && gr < sh && gc < sw;
-                const unsigned gi = (unsigned)gr * usp + (unsigned)gc;
-#pragma unroll
-                for (int s = 0; s < 5; s++) v[it][s] = in ? __ldg(src + (gi + (unsigned)s * uosz)) : 0.f;
-            }
-#pragma unroll
-            for (int it = 0; it < 3; it++)
-                if (si[it] >= 0) {
-#pragma unroll
-                    for (int s = 0; s < 5; s++) flat[s * (kNmsR * kNmsC) + si[it]] = v[it][s];
-                }
+        for (int it = 0; it < 8; it++) {
+            const int e = tid + 256 * it;
+            const int rr = e / (kNmsC / 4), c4 = e - rr * (kNmsC / 4);  // rr = layer * kNmsR + row
+            const int layer = rr / kNmsR, r = rr - layer * kNmsR;
+            const int gr = row0 + r, gc = col0 + 4 * c4;
+            const bool in = layer < 5 && r < NR && gr < sh && gc < (int)usp;
+            si[it] = (layer < 5 && r < NR) ? e : -1;
+            // clamped address + select instead of a branch around the load
+            const unsigned gi = in ? (unsigned)layer * uosz + (unsigned)gr * usp + (unsigned)gc : 0u;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src + gi));
+            v[it] = in ? t : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+#pragma unroll
+        for (int it = 0; it < 8; it++)
+            if (si[it] >= 0) flat[si[it]] = v[it];
     }
     __syncthreads();
 
