@@ -205,7 +205,7 @@ __device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict
 }
 
 // grid (tiles_x * tiles_y, nframes), 256 threads, 24 KB static shared memory
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int tiles_x) {
     __shared__ __align__(16) int patch[4 * kPlane + 16];
     const int f = blockIdx.y;
@@ -213,14 +213,28 @@ hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
     const int* I = Ibase + (size_t)f * P.istride + P.ip;
     const int X0 = 2 * kTW * tx - kHalo, Y0 = 2 * kTH * ty - kHalo;
     // stage: 64 rows x 24 int4; (x0,x2) go to the even-column plane, (x1,x3) to the odd one
-    for (int t = threadIdx.x; t < kPH * (kPW / 4); t += 256) {
-        const int row = t / (kPW / 4), k = t - row * (kPW / 4);
-        const int y = Y0 + row, x = X0 + 4 * k;
-        int4 v = make_int4(0, 0, 0, 0);
-        if (y >= 0 && y < P.ih && x >= 0 && x + 3 < P.ip) v = __ldg(reinterpret_cast<const int4*>(I + (size_t)y * P.ip + x));
-        int* dst = patch + (row & 1) * kRowPar + (row >> 1) * kQW + 2 * k;
-        *reinterpret_cast<int2*>(dst) = make_int2(v.x, v.z);
-        *reinterpret_cast<int2*>(dst + kPlane) = make_int2(v.y, v.w);
+    // (1536 int4 = 6 per thread, all six loads in flight before the first store waits on one: as a plain loop every
+    // position was its own memory round trip)
+    static_assert(kPH * (kPW / 4) == 6 * 256, "staging assumes 6 int4 per thread");
+    {
+        int4 v[6];
+#pragma unroll
+        for (int it = 0; it < 6; it++) {
+            const int t = threadIdx.x + 256 * it;
+            const int row = t / (kPW / 4), k = t - row * (kPW / 4);
+            const int y = Y0 + row, x = X0 + 4 * k;
+            const bool in = y >= 0 && y < P.ih && x >= 0 && x + 3 < P.ip;
+            const int4 ld = __ldg(reinterpret_cast<const int4*>(I + (in ? (size_t)y * P.ip + x : (size_t)0)));
+            v[it] = in ? ld : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int it = 0; it < 6; it++) {
+            const int t = threadIdx.x + 256 * it;
+            const int row = t / (kPW / 4), k = t - row * (kPW / 4);
+            int* dst = patch + (row & 1) * kRowPar + (row >> 1) * kQW + 2 * k;
+            *reinterpret_cast<int2*>(dst) = make_int2(v[it].x, v[it].z);
+            *reinterpret_cast<int2*>(dst + kPlane) = make_int2(v[it].y, v[it].w);
+        }
     }
     __syncthreads();
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;

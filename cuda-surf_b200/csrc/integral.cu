@@ -83,15 +83,19 @@ integral_reduce(const __grid_constant__ PipeP P, const uint8_t* __restrict__ img
     int acc[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) acc[k] = 0;
-    for (int r = warp; r < kBand; r += 8) {
-        const int y = b * kBand + r;
-        int v[8];
-        if (y < P.h) {
-            load_shifted<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane, v);
-        } else {
+    // the four rows of this warp: all loads first (one exposed latency), then the sums
+    RawRow raw[4];
 #pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = 0;
-        }
+    for (int u = 0; u < 4; u++) {
+        const int y = b * kBand + warp + 8 * u;
+        if (y < P.h) raw[u] = load_raw<ALIGNED>(img + (size_t)y * pitch, P.w, c, lane);
+        else { raw[u].lo = 0; raw[u].hi = 0; raw[u].prev0 = 0; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const int y = b * kBand + warp + 8 * u;
+        int v[8];
+        unpack_shifted(raw[u], lane, v);
         int s = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) { s += v[k]; acc[k] += v[k]; }
