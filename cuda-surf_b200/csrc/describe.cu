@@ -21,6 +21,7 @@
 namespace sb {
 
 constexpr int kWarpsPerCta = 4;
+constexpr int kRotRows = 128;  // lattice rows of the rotated descriptor: side = 2R+1 <= 63 (W = 4) ... 101 (W = 1), since sc/step < 3
 constexpr float kR255 = 0.003921568627f;
 constexpr float kWindow = 1.0471975511965976f;     // surfd.h:12
 constexpr float kSepAngle = 0.08726646259971647f;  // surfd.h:13
@@ -220,58 +221,55 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
 
 // ---------------------------------------------------------------------------------- descriptor
 
-// One sample's bilinear spread into the 2x2 nearest cells (placeInIndex, surfd.cu:1199-1271),
-// into this lane's private descriptor copy h[element*32 + lane].
-__device__ __forceinline__ void place(float* __restrict__ h, int lane, int W, int O, float mag1, int ori1, float mag2,
+// One sample's bilinear spread into the 2x2 nearest cells (placeInIndex, surfd.cu:1199-1271), into this lane's private
+// descriptor copy h[element*32 + lane]. Branch-free: a cell outside the WxW grid gets weight 0 and is redirected to a
+// per-lane dummy word (row `dummy` of h), so the 8 addresses never alias a live one and the 8 loads are issued together
+// before the 8 stores (with a branch per quadrant the updates were 8 dependent shared-memory round trips).
+__device__ __forceinline__ void place(float* __restrict__ h, int lane, int W, int O, int dummy, float mag1, int ori1, float mag2,
                                       int ori2, float rx, float cx) {
     const int ri = __float2int_rz(rx >= 0.f ? rx : __fsub_rn(rx, 1.f));
     const int ci = __float2int_rz(cx >= 0.f ? cx : __fsub_rn(cx, 1.f));
     const float rfrac = __fsub_rn(rx, __int2float_rn(ri));
     const float cfrac = __fsub_rn(cx, __int2float_rn(ci));
-    const float cfrac1 = __fsub_rn(1.f, cfrac);
-    if (ri >= 0) {
-        const float rw1 = __fmul_rn(mag1, __fsub_rn(1.f, rfrac)), rw2 = __fmul_rn(mag2, __fsub_rn(1.f, rfrac));
-        if (ci >= 0) {
-            float* e = h + ((ri * W + ci) * O) * 32 + lane;
-            e[ori1 * 32] += __fmul_rn(rw1, cfrac1);
-            e[ori2 * 32] += __fmul_rn(rw2, cfrac1);
-        }
-        if (ci + 1 < W) {
-            float* e = h + ((ri * W + ci + 1) * O) * 32 + lane;
-            e[ori1 * 32] += __fmul_rn(rw1, cfrac);
-            e[ori2 * 32] += __fmul_rn(rw2, cfrac);
-        }
-    }
-    if (ri + 1 < W) {
-        const float rw1 = __fmul_rn(mag1, rfrac), rw2 = __fmul_rn(mag2, rfrac);
-        if (ci >= 0) {
-            float* e = h + (((ri + 1) * W + ci) * O) * 32 + lane;
-            e[ori1 * 32] += __fmul_rn(rw1, cfrac1);
-            e[ori2 * 32] += __fmul_rn(rw2, cfrac1);
-        }
-        if (ci + 1 < W) {
-            float* e = h + (((ri + 1) * W + ci + 1) * O) * 32 + lane;
-            e[ori1 * 32] += __fmul_rn(rw1, cfrac);
-            e[ori2 * 32] += __fmul_rn(rw2, cfrac);
-        }
-    }
+    const bool r0ok = ri >= 0, r1ok = ri + 1 < W, c0ok = ci >= 0, c1ok = ci + 1 < W;
+    const float rw0 = __fsub_rn(1.f, rfrac), rw1 = rfrac, cw0 = __fsub_rn(1.f, cfrac), cw1 = cfrac;
+    const int e00 = (r0ok && c0ok) ? (ri * W + ci) * O : dummy;
+    const int e01 = (r0ok && c1ok) ? (ri * W + ci + 1) * O : dummy;
+    const int e10 = (r1ok && c0ok) ? ((ri + 1) * W + ci) * O : dummy;
+    const int e11 = (r1ok && c1ok) ? ((ri + 1) * W + ci + 1) * O : dummy;
+    float* p[8] = {h + (e00 + ori1) * 32 + lane, h + (e00 + ori2) * 32 + lane, h + (e01 + ori1) * 32 + lane, h + (e01 + ori2) * 32 + lane,
+                   h + (e10 + ori1) * 32 + lane, h + (e10 + ori2) * 32 + lane, h + (e11 + ori1) * 32 + lane, h + (e11 + ori2) * 32 + lane};
+    const float a0 = __fmul_rn(mag1, rw0), b0 = __fmul_rn(mag2, rw0), a1 = __fmul_rn(mag1, rw1), b1 = __fmul_rn(mag2, rw1);
+    const float add[8] = {__fmul_rn(a0, cw0), __fmul_rn(b0, cw0), __fmul_rn(a0, cw1), __fmul_rn(b0, cw1),
+                          __fmul_rn(a1, cw0), __fmul_rn(b1, cw0), __fmul_rn(a1, cw1), __fmul_rn(b1, cw1)};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = *p[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) *p[k] = __fadd_rn(v[k], add[k]);
 }
 
 // Rotated descriptor (describeApproxWithoutNormalization + addSample, surfd.cu:2391-2444, 1984-2015): the sampling lattice
 // stays axis-aligned in the image, the window coordinates (rpos, cpos) are rotated by the keypoint's orientation, so rows
 // and columns do not separate as in the upright kernel; a warp walks the (2R+1)^2 lattice 32 samples at a time.
-// grid (ctas, nframes), 4 warps per CTA, dynamic smem = 4 * NF*32 floats + 40 floats.
+// grid (ctas, nframes), 4 warps per CTA, dynamic smem = 4 * (160 ints + (NF+8)*32 floats) + 40 floats.
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
                         long long desc_stride) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz, O = P.orient_size;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* s_lut2 = smem + kWarpsPerCta * NF * 32;
+    // layout: [4 warps][2 * kRotRows + 32] row tables (first column, dense start) | [4 warps][(NF+8)*32] private descriptor
+    // copies | lut2[40]
+    int* rjlo = reinterpret_cast<int*>(smem) + warp * (2 * kRotRows + 32);
+    int* rstart = rjlo + kRotRows;  // kRotRows + 1 entries
+    float* hbase = smem + kWarpsPerCta * (2 * kRotRows + 32);
+    const int hrows = NF + 8;  // + the dummy rows of place()
+    float* s_lut2 = hbase + kWarpsPerCta * hrows * 32;
     for (int t = threadIdx.x; t < 40; t += blockDim.x) s_lut2[t] = P.lut2[t];
     __syncthreads();
-    float* h = smem + warp * NF * 32;
+    float* h = hbase + warp * hrows * 32;
     const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
     const int* I = Ibase + (size_t)f * P.istride + P.ip;
     const sb_point* pts = points + (size_t)f * pts_stride;
@@ -279,7 +277,7 @@ describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     const float fW = __int2float_rn(W);
 
     for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
-        for (int e = 0; e < NF; e++) h[e * 32 + lane] = 0.f;
+        for (int e = 0; e < hrows; e++) h[e * 32 + lane] = 0.f;
         float x = pts[pi].x, y = pts[pi].y;
         if (P.doubled) { x = __fadd_rn(x, x); y = __fadd_rn(y, y); }  // surfd.cu:2406-2411
         const float sc = __fmul_rn(P.doubled ? 3.3f : 1.65f, pts[pi].scale);
@@ -295,34 +293,94 @@ describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__
         const float fracc = __fmaf_rn(-sine, fy, __fmul_rn(cose, fx));
         const float fracr = __fmaf_rn(cose, fy, __fmul_rn(sine, fx));
         const int R = __float2int_rn(__fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(1.4f, spacing), __int2float_rn(W + 1)), 0.5f), fstep));
-        const int side = 2 * R + 1, total = side * side;
-        const float inv_side = 1.f / (float)side;
+        const int side = 2 * R + 1;
         // |rpos| < (W+1)/2 is the window test -1 < rpos + wofs < W; about half of the lattice (the corners of the bounding
         // square of the rotated window) fails it by a wide margin and is rejected on the numerators, before the two IEEE
         // divisions. The margin keeps the exact test below the only one that decides.
         const float far_lim = __fmul_rn(__fmaf_rn(fW, 0.5f, 0.51f), spacing);
-        for (int qi = lane; qi < total; qi += 32) {
-            const int ii = (int)(((float)qi + 0.5f) * inv_side);
-            const int i = ii - R, j = qi - ii * side - R;
-            const float fi = __int2float_rn(i), fj = __int2float_rn(j);
-            const float nr = __fmaf_rn(fstep, __fmaf_rn(cose, fi, __fmul_rn(sine, fj)), -fracr);
-            const float nc = __fmaf_rn(fstep, __fmaf_rn(-sine, fi, __fmul_rn(cose, fj)), -fracc);
-            if (fabsf(nr) > far_lim || fabsf(nc) > far_lim) continue;
-            const float rpos = __fdiv_rn(nr, spacing), cpos = __fdiv_rn(nc, spacing);
-            const float rx = __fadd_rn(rpos, wofs), cx = __fadd_rn(cpos, wofs);
-            if (!(rx > -1.f && rx < fW && cx > -1.f && cx < fW)) continue;
-            const int r = iyc + i * step, c = ixc + j * step;
-            if (!(r >= 1 + S && r < P.ih - 1 - S && c >= 1 + S && c < P.iw - 1 - S)) continue;
-            const float weight = s_lut2[__float2int_rz(__fmaf_rn(rpos, rpos, __fmul_rn(cpos, cpos)))];
-            const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_x(I, P.ip, c, r, S))), kR255);
-            const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_y(I, P.ip, c, r, S))), kR255);
-            const float dx = __fmaf_rn(cose, a, __fmul_rn(sine, b));
-            const float dy = __fmaf_rn(sine, a, -__fmul_rn(cose, b));
-            if (O == 4) {
-                place(h, lane, W, O, dx, (dx < 0.f ? 0 : 1), dy, (dy < 0.f ? 2 : 3), rx, cx);
-            } else {
-                place(h, lane, W, O, dx, (dy < 0.f ? 0 : 1), fabsf(dx), (dy < 0.f ? 2 : 3), rx, cx);
-                place(h, lane, W, O, dy, (dx < 0.f ? 4 : 5), fabsf(dy), (dx < 0.f ? 6 : 7), rx, cx);
+        // Enumeration of the lattice. The rotated window covers about half of its bounding (2R+1)^2 lattice, so walking
+        // all of it left half of every warp idle (and the rejection tests alone were half of the instructions). Here each
+        // lattice ROW gets the interval of columns that can pass -- |nr|, |nc| <= far_lim are linear in j, plus the image
+        // border in c, widened by one column on both sides against rounding -- a warp scan of the interval lengths makes a
+        // dense index, and the warp walks that: a superset of the valid points, in lattice order, ~95 % of the lanes
+        // passing the exact tests (unchanged) below.
+        if (side > kRotRows) __trap();  // cannot happen: R = rn(1.4 * 6 sc (W+1)/W / step) with sc / step < 3
+        int total = 0;
+        {
+            const float A = __fmul_rn(fstep, sine), B = __fmul_rn(fstep, cose);
+            int cnt[kRotRows / 32];
+#pragma unroll
+            for (int u = 0; u < kRotRows / 32; u++) {
+                const int ii = lane + 32 * u;
+                int lo = 0, hi = -1;
+                if (ii < side) {
+                    const float fi = __int2float_rn(ii - R);
+                    const float cr = B * fi - fracr, cc = -A * fi - fracc;  // nr = cr + A j, nc = cc + B j
+                    float flo = (float)-R, fhi = (float)R;
+                    if (fabsf(A) > 1e-6f) {
+                        const float t0 = (-far_lim - cr) / A, t1 = (far_lim - cr) / A;
+                        flo = fmaxf(flo, fminf(t0, t1)); fhi = fminf(fhi, fmaxf(t0, t1));
+                    } else if (fabsf(cr) > far_lim) { fhi = flo - 4.f; }
+                    if (fabsf(B) > 1e-6f) {
+                        const float t0 = (-far_lim - cc) / B, t1 = (far_lim - cc) / B;
+                        flo = fmaxf(flo, fminf(t0, t1)); fhi = fminf(fhi, fmaxf(t0, t1));
+                    } else if (fabsf(cc) > far_lim) { fhi = flo - 4.f; }
+                    // image border: 1 + S <= ixc + j*step < iw - 1 - S
+                    flo = fmaxf(flo, (float)(1 + S - ixc) / fstep);
+                    fhi = fminf(fhi, (float)(P.iw - 2 - S - ixc) / fstep);
+                    const int r = iyc + (ii - R) * step;
+                    if (!(r >= 1 + S && r < P.ih - 1 - S)) fhi = flo - 4.f;
+                    lo = max(-R, (int)floorf(flo) - 1);
+                    hi = min(R, (int)ceilf(fhi) + 1);
+                }
+                cnt[u] = max(0, hi - lo + 1);
+                rjlo[ii] = lo;
+            }
+            // exclusive scan over the rows (row ii = lane + 32 u)
+            int run = 0;
+#pragma unroll
+            for (int u = 0; u < kRotRows / 32; u++) {
+                int incl = cnt[u];
+#pragma unroll
+                for (int o2 = 1; o2 < 32; o2 <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o2);
+                    if (lane >= o2) incl += t;
+                }
+                rstart[lane + 32 * u] = run + incl - cnt[u];
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            total = run;
+            if (lane == 0) rstart[kRotRows] = total;
+        }
+        __syncwarp();
+        int row = 0;
+        for (int d0 = 0; d0 < total; d0 += 32) {
+            const int d = d0 + lane;
+            if (d < total) {
+                while (d >= rstart[row + 1]) row++;
+                const int i = row - R, j = rjlo[row] + (d - rstart[row]);
+                const float fi = __int2float_rn(i), fj = __int2float_rn(j);
+                const float nr = __fmaf_rn(fstep, __fmaf_rn(cose, fi, __fmul_rn(sine, fj)), -fracr);
+                const float nc = __fmaf_rn(fstep, __fmaf_rn(-sine, fi, __fmul_rn(cose, fj)), -fracc);
+                if (!(fabsf(nr) > far_lim || fabsf(nc) > far_lim)) {
+                    const float rpos = __fdiv_rn(nr, spacing), cpos = __fdiv_rn(nc, spacing);
+                    const float rx = __fadd_rn(rpos, wofs), cx = __fadd_rn(cpos, wofs);
+                    const int r = iyc + i * step, c = ixc + j * step;
+                    if (rx > -1.f && rx < fW && cx > -1.f && cx < fW && r >= 1 + S && r < P.ih - 1 - S && c >= 1 + S &&
+                        c < P.iw - 1 - S) {
+                        const float weight = s_lut2[__float2int_rz(__fmaf_rn(rpos, rpos, __fmul_rn(cpos, cpos)))];
+                        const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_x(I, P.ip, c, r, S))), kR255);
+                        const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_y(I, P.ip, c, r, S))), kR255);
+                        const float dx = __fmaf_rn(cose, a, __fmul_rn(sine, b));
+                        const float dy = __fmaf_rn(sine, a, -__fmul_rn(cose, b));
+                        if (O == 4) {
+                            place(h, lane, W, O, NF, dx, (dx < 0.f ? 0 : 1), dy, (dy < 0.f ? 2 : 3), rx, cx);
+                        } else {
+                            place(h, lane, W, O, NF, dx, (dy < 0.f ? 0 : 1), fabsf(dx), (dy < 0.f ? 2 : 3), rx, cx);
+                            place(h, lane, W, O, NF, dy, (dx < 0.f ? 4 : 5), fabsf(dy), (dx < 0.f ? 6 : 7), rx, cx);
+                        }
+                    }
+                }
             }
         }
         __syncwarp();
@@ -652,7 +710,7 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
             describe_upright_kernel<8><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
         }
     } else {
-        const size_t smem = ((size_t)kWarpsPerCta * P.nfeatures * 32 + 40) * sizeof(float);
+        const size_t smem = ((size_t)kWarpsPerCta * (2 * kRotRows + 32) + (size_t)kWarpsPerCta * (P.nfeatures + 8) * 32 + 40) * sizeof(float);
         cudaFuncSetAttribute(describe_rotated_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         describe_rotated_kernel<<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
     }
