@@ -198,22 +198,27 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
             S.ws[i] = ws; S.was[i] = was;
         }
         __syncwarp();
-        // phase D: the reference's tournament arg-max (64-wide tree, 8-wide tree at 64, strict <)
-        if (lane == 0) {
+        // phase D: the reference's tournament arg-max (64-wide tree, 8-wide tree at 64, strict <). The pairs of one tree
+        // level are disjoint, so a level is one step of the warp (as one lane's loop the 71 compare/copy steps were a
+        // fifth of the kernel's instructions and a serial chain of shared-memory round trips).
+        {
             int residual = kNBin, offset = 0;
             while (residual > 0) {
                 int zn = 1;
                 while (zn * 2 <= residual) zn *= 2;
-                for (int stride = zn / 2; stride > 0; stride >>= 1)
-                    for (int t = 0; t < stride; t++) {
+                for (int stride = zn / 2; stride > 0; stride >>= 1) {
+                    for (int t = lane; t < stride; t += 32) {
                         const int id1 = t + offset, id2 = id1 + stride;
                         if (S.ws[id1] < S.ws[id2]) { S.ws[id1] = S.ws[id2]; S.was[id1] = S.was[id2]; }
                     }
-                if (S.ws[0] < S.ws[offset]) { S.ws[0] = S.ws[offset]; S.was[0] = S.was[offset]; }
+                    __syncwarp();
+                }
+                if (lane == 0 && S.ws[0] < S.ws[offset]) { S.ws[0] = S.ws[offset]; S.was[0] = S.was[offset]; }
+                __syncwarp();
                 residual -= zn;
                 offset += zn;
             }
-            pts[pi].ori = __fdiv_rn(S.was[0], S.ws[0]);
+            if (lane == 0) pts[pi].ori = __fdiv_rn(S.was[0], S.ws[0]);
         }
         __syncwarp();
     }
