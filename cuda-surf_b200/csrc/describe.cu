@@ -444,7 +444,7 @@ template <int O>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
 describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
-                        long long desc_stride) {
+                        long long desc_stride, int* __restrict__ work) {
     extern __shared__ __align__(16) float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -467,7 +467,9 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     const float fW = __int2float_rn(W);
     const int half = lane >> 4, jl = lane & 15;
 
-    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
+    // a warp's first keypoint is fixed, the following ones come from a per-frame counter (zero on entry): keypoints cost
+    // 2 or 3 passes, and with one or two per warp (single frame) a static split left the machine waiting for the unlucky warps
+    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n;) {
         const float x = pts[pi].x, y = pts[pi].y;
         const KpGeom kg = kp_geom(x, y, pts[pi].scale, W, P.mag_factor, P.doubled);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};  // descriptor elements lane, lane+32, ... (un-normalised)
@@ -688,12 +690,15 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
             if (e < NF) d[e] = __fmul_rn(v[u], inv);
         }
         __syncwarp();
+        int nxt = 0;
+        if (lane == 0) nxt = gridDim.x * kWarpsPerCta + atomicAdd(work + f, 1);
+        pi = __shfl_sync(0xffffffffu, nxt, 0);
     }
 }
 
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
-                            cudaStream_t st) {
+                            int* d_work, cudaStream_t st) {
     const int maxn = fixed_count >= 0 ? fixed_count : P.max_pts;
     if (maxn <= 0 || nframes <= 0) return cudaSuccess;
     const int need = (maxn + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -709,10 +714,10 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
         const size_t smem = ((size_t)kWarpsPerCta * (P.desc_wsz * P.orient_size + P.desc_wsz) * kTS + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
         if (P.orient_size == 4) {
             cudaFuncSetAttribute(describe_upright_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            describe_upright_kernel<4><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+            describe_upright_kernel<4><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work);
         } else {
             cudaFuncSetAttribute(describe_upright_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            describe_upright_kernel<8><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+            describe_upright_kernel<8><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work);
         }
     } else {
         const size_t smem = ((size_t)kWarpsPerCta * (2 * kRotRows + 32) + (size_t)kWarpsPerCta * (P.nfeatures + 8) * 32 + 40) * sizeof(float);
