@@ -118,8 +118,9 @@ cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const
                        int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st);
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
-                            int* d_work /* one zeroed int per frame */, cudaStream_t st);
-cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, cudaStream_t st);
+                            int* d_work, int* d_work_orient /* one zeroed int per frame each */, cudaStream_t st);
+cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, int* d_work_orient,
+                                cudaStream_t st);
 // grow-only device scratch of the matcher (split-bf16 operands, per-split group top-2), owned by the context
 struct MatchScratch {
     void* a = nullptr; void* b = nullptr; void* part = nullptr;

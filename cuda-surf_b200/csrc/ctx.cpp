@@ -253,7 +253,7 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     c->cand_cap = (int)std::min<long long>(4LL * P.max_pts, 1LL << 24);
     ok(cudaMalloc((void**)&c->d_cand, sizeof(unsigned) * (size_t)c->cand_cap * B));
     ok(cudaMalloc((void**)&c->d_cand_count, sizeof(int) * B));
-    ok(cudaMalloc((void**)&c->d_work, sizeof(int) * B));
+    ok(cudaMalloc((void**)&c->d_work, sizeof(int) * 2 * B));  // [0, B): descriptor pass, [B, 2B): orientation pass
     if (P.doubled) {
         c->up_pitch = align_up(P.w, 128);
         ok(cudaMalloc((void**)&c->d_up, (size_t)c->up_pitch * P.h * B));
@@ -268,7 +268,7 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
         ok(cudaMemsetAsync(c->d_resp, 0, rsz, c->stream));
         ok(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * B, c->stream));
         ok(cudaMemsetAsync(c->d_cand_count, 0, sizeof(int) * B, c->stream));
-        ok(cudaMemsetAsync(c->d_work, 0, sizeof(int) * B, c->stream));
+        ok(cudaMemsetAsync(c->d_work, 0, sizeof(int) * 2 * B, c->stream));
         ok(cudaStreamSynchronize(c->stream));
     }
     if (e != cudaSuccess) {
@@ -327,11 +327,12 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
     if (ev) CU(cudaEventRecord(ev[2], st));
     CU(launch_nms(P, nframes, integral, resp, d_points, d_counts, ctx->d_cand + (size_t)slot0 * ctx->cand_cap,
                   ctx->d_cand_count + slot0, ctx->cand_cap, st));
-    CU(launch_clamp_counts(d_counts, nframes, P.max_pts, ctx->d_cand_count + slot0, ctx->d_work + slot0, st));
+    CU(launch_clamp_counts(d_counts, nframes, P.max_pts, ctx->d_cand_count + slot0, ctx->d_work + slot0,
+                           ctx->d_work + ctx->prm.batch + slot0, st));
     if (ev) CU(cudaEventRecord(ev[3], st));
     if (d_desc)
         CU(launch_describe(P, nframes, integral, d_points, P.max_pts, d_counts, -1, d_desc,
-                           (long long)P.max_pts * P.nfeatures, ctx->sm_count, ctx->d_work + slot0, st));
+                           (long long)P.max_pts * P.nfeatures, ctx->sm_count, ctx->d_work + slot0, ctx->d_work + ctx->prm.batch + slot0, st));
     if (ev) CU(cudaEventRecord(ev[4], st));
     return SB_OK;
 }
@@ -690,7 +691,9 @@ extern "C" int sb_describe(sb_ctx* ctx, int slot, sb_point* d_points, int n, flo
     const PipeP& P = ctx->P;
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->d_work + slot, 0, sizeof(int), ctx->stream));
-    CU(launch_describe(P, 1, ctx->d_integral + (size_t)slot * P.istride, d_points, 0, nullptr, n, d_desc, 0, ctx->sm_count, ctx->d_work + slot, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_work + ctx->prm.batch + slot, 0, sizeof(int), ctx->stream));
+    CU(launch_describe(P, 1, ctx->d_integral + (size_t)slot * P.istride, d_points, 0, nullptr, n, d_desc, 0, ctx->sm_count, ctx->d_work + slot,
+                       ctx->d_work + ctx->prm.batch + slot, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }

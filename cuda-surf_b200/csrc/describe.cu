@@ -64,7 +64,7 @@ struct OrientSmem {
 // in lattice scan order (the reference's shared-memory atomics make its sums order-dependent).
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb_point* __restrict__ points,
-              long long pts_stride, const int* __restrict__ counts, int fixed_count) {
+              long long pts_stride, const int* __restrict__ counts, int fixed_count, int* __restrict__ work) {
     __shared__ OrientSmem sm[kWarpsPerCta];
     __shared__ float s_lut1[83];
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,7 +75,7 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
     sb_point* pts = points + (size_t)f * pts_stride;
     OrientSmem& S = sm[warp];
 
-    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
+    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n;) {  // first keypoint fixed, the next ones from the frame's counter
         float x = pts[pi].x, y = pts[pi].y, scale = pts[pi].scale;
         if (P.doubled) { x = __fadd_rn(x, x); y = __fadd_rn(y, y); scale = __fadd_rn(scale, scale); }  // surfd.cu:1734-1739
         const int hs = __float2int_rz(__fmaf_rn(2.f, scale, 1.6f));
@@ -221,6 +221,9 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
             if (lane == 0) pts[pi].ori = __fdiv_rn(S.was[0], S.ws[0]);
         }
         __syncwarp();
+        int nxt = 0;
+        if (lane == 0) nxt = gridDim.x * kWarpsPerCta + atomicAdd(work + f, 1);
+        pi = __shfl_sync(0xffffffffu, nxt, 0);
     }
 }
 
@@ -261,7 +264,7 @@ __device__ __forceinline__ void place(float* __restrict__ h, int lane, int W, in
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
-                        long long desc_stride) {
+                        long long desc_stride, int* __restrict__ work) {
     extern __shared__ __align__(16) float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz, O = P.orient_size;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,7 +284,7 @@ describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     float* dout = desc + (size_t)f * desc_stride;
     const float fW = __int2float_rn(W);
 
-    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n; pi += gridDim.x * kWarpsPerCta) {
+    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n;) {  // first keypoint fixed, the next ones from the frame's counter
         for (int e = 0; e < hrows; e++) h[e * 32 + lane] = 0.f;
         float x = pts[pi].x, y = pts[pi].y;
         if (P.doubled) { x = __fadd_rn(x, x); y = __fadd_rn(y, y); }  // surfd.cu:2406-2411
@@ -412,6 +415,9 @@ describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__
             if (e < NF) d[e] = __fmul_rn(v[u], inv);
         }
         __syncwarp();
+        int nxt = 0;
+        if (lane == 0) nxt = gridDim.x * kWarpsPerCta + atomicAdd(work + f, 1);
+        pi = __shfl_sync(0xffffffffu, nxt, 0);
     }
 }
 
@@ -698,7 +704,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
 
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
-                            int* d_work, cudaStream_t st) {
+                            int* d_work, int* d_work_orient, cudaStream_t st) {
     const int maxn = fixed_count >= 0 ? fixed_count : P.max_pts;
     if (maxn <= 0 || nframes <= 0) return cudaSuccess;
     const int need = (maxn + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -709,7 +715,8 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     if (ctas < 1) ctas = 1;
     if (ctas > need) ctas = need;
     const dim3 grid(ctas, nframes), block(kWarpsPerCta * 32);
-    if (!P.upright) orient_kernel<<<grid, block, 0, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count);
+    // (the orientation pass has its own counters: d_work_orient)
+    if (!P.upright) orient_kernel<<<grid, block, 0, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_work_orient);
     if (P.upright) {
         const size_t smem = ((size_t)kWarpsPerCta * (P.desc_wsz * P.orient_size + P.desc_wsz) * kTS + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
         if (P.orient_size == 4) {
@@ -722,7 +729,7 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     } else {
         const size_t smem = ((size_t)kWarpsPerCta * (2 * kRotRows + 32) + (size_t)kWarpsPerCta * (P.nfeatures + 8) * 32 + 40) * sizeof(float);
         cudaFuncSetAttribute(describe_rotated_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        describe_rotated_kernel<<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride);
+        describe_rotated_kernel<<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work);
     }
     return cudaGetLastError();
 }
