@@ -30,6 +30,7 @@ constexpr double kPi = 3.14159265358979323846;     // M_PI (double in the refere
 constexpr int kORadius = 9;                        // surfd.h:15
 constexpr int kOSide = 2 * kORadius + 1;           // 19
 constexpr int kOSamples = kOSide * kOSide;         // 361
+constexpr int kOValid = 253;                       // lattice points with x1^2 + y1^2 < 82 (surfd.cu:1760), walked densely
 constexpr int kPasz = kNBin + 2 * kHwn;            // 84
 
 // ---------------------------------------------------------------------------------- orientation
@@ -67,8 +68,20 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
               long long pts_stride, const int* __restrict__ counts, int fixed_count, int* __restrict__ work) {
     __shared__ OrientSmem sm[kWarpsPerCta];
     __shared__ float s_lut1[83];
+    __shared__ short s_tab[kOValid + 3];  // lattice index qi of the d-th point inside the circle, ascending
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int t = threadIdx.x; t < 83; t += blockDim.x) s_lut1[t] = P.lut1[t];
+    if (warp == 0) {
+        int nv = 0;
+        for (int q0 = 0; q0 < kOSamples; q0 += 32) {
+            const int qi = q0 + lane;
+            const int y1 = qi / kOSide - kORadius, x1 = qi % kOSide - kORadius;
+            const bool in = qi < kOSamples && y1 * y1 + x1 * x1 < 82;
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) s_tab[nv + __popc(m & ((1u << lane) - 1u))] = (short)qi;
+            nv += __popc(m);
+        }
+    }
     __syncthreads();
     const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
     const int* I = Ibase + (size_t)f * P.istride + P.ip;
@@ -82,13 +95,15 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
         const int st = __float2int_rz(__fadd_rn(scale, 0.8f));
         const int ixc = __float2int_rn(x), iyc = __float2int_rn(y);
         // phase A: Haar responses on the 19x19 lattice
-        for (int qi = lane; qi < kOSamples; qi += 32) {
+        // (the 253 points inside the circle only, in lattice order: every array below is indexed by that dense position)
+        for (int di = lane; di < kOValid; di += 32) {
+            const int qi = s_tab[di];
             const int y1 = qi / kOSide - kORadius, x1 = qi % kOSide - kORadius;
             const int xx = ixc + x1 * st, yy = iyc + y1 * st;
             short hid = -1;
             float angle = 0.f, psum = 0.f;
             const int distsq = y1 * y1 + x1 * x1;
-            if (yy + hs + 2 < P.ih && yy - hs > -1 && xx + hs + 2 < P.iw && xx - hs > -1 && distsq < 82) {
+            if (yy + hs + 2 < P.ih && yy - hs > -1 && xx + hs + 2 < P.iw && xx - hs > -1) {
                 const float dx = __fmul_rn(__int2float_rn(haar_x(I, P.ip, xx, yy, hs)), kR255);
                 const float dy = __fmul_rn(__int2float_rn(haar_y(I, P.ip, xx, yy, hs)), kR255);
                 const float mag = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
@@ -98,7 +113,7 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
                     psum = __fmul_rn(s_lut1[distsq], mag);
                 }
             }
-            S.hid[qi] = hid; S.ang[qi] = angle; S.ps[qi] = psum;
+            S.hid[di] = hid; S.ang[di] = angle; S.ps[di] = psum;
         }
         __syncwarp();
         // phase B: per-bin sums, each bin summed in lattice scan order (the order of the CPU restatement; the
@@ -107,9 +122,9 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
         // only the samples of its own bins (3.5 on average) instead of testing all 361 against each bin.
         for (int b = lane; b < kNBin; b += 32) S.hist[b] = 0;
         __syncwarp();
-        for (int q0 = 0; q0 < kOSamples; q0 += 32) {  // B1: counts
+        for (int q0 = 0; q0 < kOValid; q0 += 32) {  // B1: counts
             const int qi = q0 + lane;
-            const int hid = qi < kOSamples ? (int)S.hid[qi] : -1;
+            const int hid = qi < kOValid ? (int)S.hid[qi] : -1;
             const unsigned grp = __match_any_sync(0xffffffffu, hid >= 0 ? hid : 128 + lane);
             if (hid >= 0 && (grp & ((1u << lane) - 1u)) == 0) S.hist[hid] += __popc(grp);  // group leader; bins are distinct
             __syncwarp();
@@ -129,9 +144,9 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
             if (lane + 64 < kNBin) { S.start[lane + 64] = tot0 + tot1 + s2 - c2; S.fill[lane + 64] = tot0 + tot1 + s2 - c2; }
         }
         __syncwarp();
-        for (int q0 = 0; q0 < kOSamples; q0 += 32) {  // B2: stable scatter of the sample indices
+        for (int q0 = 0; q0 < kOValid; q0 += 32) {  // B2: stable scatter of the sample indices
             const int qi = q0 + lane;
-            const int hid = qi < kOSamples ? (int)S.hid[qi] : -1;
+            const int hid = qi < kOValid ? (int)S.hid[qi] : -1;
             const unsigned grp = __match_any_sync(0xffffffffu, hid >= 0 ? hid : 128 + lane);
             const int rank = __popc(grp & ((1u << lane) - 1u));
             int base = 0;
