@@ -723,10 +723,10 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     const int maxn = fixed_count >= 0 ? fixed_count : P.max_pts;
     if (maxn <= 0 || nframes <= 0) return cudaSuccess;
     const int need = (maxn + kWarpsPerCta - 1) / kWarpsPerCta;
-    // blockIdx.x runs fastest, so ~2 CTAs per SM per frame keeps only a few frames' integral images
-    // live at a time (L2-resident) while still covering the machine for a single frame
+    // blockIdx.x runs fastest, so 1-2 CTAs per SM per frame keep only a few frames' integral images
+    // live at a time (L2-resident; measured: 1 is best from 32 frames, 2 at 8) while still covering the machine for a single frame
     // (a single frame or a small batch fills the machine instead: 5 resident CTAs per SM)
-    int ctas = sm_count * (nframes >= 5 ? 2 : (nframes >= 3 ? 3 : 5));
+    int ctas = sm_count * (nframes >= 32 ? 1 : nframes >= 5 ? 2 : (nframes >= 3 ? 3 : 5));
     if (ctas < 1) ctas = 1;
     if (ctas > need) ctas = need;
     const dim3 grid(ctas, nframes), block(kWarpsPerCta * 32);
