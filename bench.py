@@ -197,7 +197,7 @@ def run_ours(args, rank, world, local_rank, dist):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        kmap = {"describe": "describe_upright_kernel<4>", "nms": "nms_scan_kernel", "hessian": "hessian_o0_kernel"}
+        kmap = {"describe": "describe_upright_kernel<4>", "nms": "nms_scan_tile_kernel", "hessian": "hessian_o0_kernel"}
         if tj.get("batch") == B and names[top] in kmap:
             traffic = tj["kernels"][kmap[names[top]]]["traffic_bytes"]
     except Exception:
