@@ -248,7 +248,9 @@ def run_ours(args, rank, world, local_rank, dist):
     if dist is not None:
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
     e2e = {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
-           "d2h_bytes_per_step": int(4 * B + nk * 48 + nk * nf * 4),
+           # counts + one strided copy per array, as wide as the batch's largest count (what sb_wait_batch_host moves)
+           "d2h_bytes_per_step": int(4 * B + B * int(h_cnt.max().item()) * (48 + nf * 4)),
+           "d2h_result_bytes_per_step": int(4 * B + nk * 48 + nk * nf * 4),
            "api": "sb_submit_batch_host / sb_wait_batch_host, three batches in flight, pinned host buffers",
            "synchronous_call_value": B * world / float(ts.item())}
 

@@ -570,14 +570,20 @@ extern "C" int sb_wait_batch_host(sb_ctx* ctx, int ticket, sb_point* h_points, i
         const int f0 = J.first[k], nf = J.first[k + 1] - f0;
         CU(cudaEventSynchronize(J.ev_done[k]));  // counts of chunk k are on the host; later chunks keep running
         CU(cudaStreamWaitEvent(ctx->s_d2h, J.ev_done[k], 0));
+        // Only the keypoints that exist travel: one strided copy per array and chunk, as wide as the chunk's largest
+        // count (a copy per frame -- 128 per 64-frame batch -- spent more time on DMA set-up than on data). Entries past a
+        // frame's own count, up to that width, are overwritten with unspecified values.
+        int nmax = 0;
         for (int f = f0; f < f0 + nf; f++) {
             const int n = h_counts[f] = J.h_counts[f];
-            if (n <= 0) continue;  // only the keypoints that exist travel
-            CU(cudaMemcpyAsync(h_points + f * pstride, J.d_pts + f * pstride, sizeof(sb_point) * n, cudaMemcpyDeviceToHost, ctx->s_d2h));
-            if (h_desc)
-                CU(cudaMemcpyAsync(h_desc + f * dstride_f, J.d_desc + f * dstride_f, sizeof(float) * (size_t)n * P.nfeatures,
-                                   cudaMemcpyDeviceToHost, ctx->s_d2h));
+            nmax = n > nmax ? n : nmax;
         }
+        if (nmax <= 0) continue;
+        CU(cudaMemcpy2DAsync(h_points + f0 * pstride, sizeof(sb_point) * pstride, J.d_pts + f0 * pstride, sizeof(sb_point) * pstride,
+                             sizeof(sb_point) * (size_t)nmax, nf, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        if (h_desc)
+            CU(cudaMemcpy2DAsync(h_desc + f0 * dstride_f, sizeof(float) * dstride_f, J.d_desc + f0 * dstride_f, sizeof(float) * dstride_f,
+                                 sizeof(float) * (size_t)nmax * P.nfeatures, nf, cudaMemcpyDeviceToHost, ctx->s_d2h));
     }
     CU(cudaStreamSynchronize(ctx->s_d2h));
     return SB_OK;

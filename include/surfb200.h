@@ -133,7 +133,9 @@ int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, sb_p
 /* The same in two halves, for a caller that streams batches: sb_submit_batch_host enqueues the uploads and kernels of a
  * batch and returns a ticket (at most three outstanding); sb_wait_batch_host downloads that batch's counts, points and
  * descriptors and returns when they are in the caller's buffers. With two batches submitted ahead, batch k downloads
- * while batch k+1 computes and batch k+2 uploads. h_images must stay valid until the ticket has been waited for.     */
+ * while batch k+1 computes and batch k+2 uploads. h_images must stay valid until the ticket has been waited for.
+ * h_points [nframes][max_pts], h_desc [nframes][max_pts][nfeatures]: entries [0, h_counts[f]) of frame f are results;
+ * entries past a frame's own count (up to the largest count of its chunk) are overwritten with unspecified values.    */
 int sb_submit_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, int want_desc, int* ticket);
 int sb_wait_batch_host(sb_ctx* ctx, int ticket, sb_point* h_points, int* h_counts, float* h_desc);
 int sb_sync(sb_ctx* ctx);
