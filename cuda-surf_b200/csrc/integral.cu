@@ -54,11 +54,6 @@ __device__ __forceinline__ void unpack_shifted(const RawRow& q, int lane, int (&
     v[7] = (int)__byte_perm(hi, 0, 0x4442);
 }
 
-template <bool ALIGNED>
-__device__ __forceinline__ void load_shifted(const uint8_t* __restrict__ row, int w, int c, int lane, int (&v)[8]) {
-    unpack_shifted(load_raw<ALIGNED>(row, w, c, lane), lane, v);
-}
-
 __device__ __forceinline__ int warp_sum(int v) { return __reduce_add_sync(0xffffffffu, v); }  // one REDUX.SUM
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
