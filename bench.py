@@ -305,7 +305,7 @@ def run_ours(args, rank, world, local_rank, dist):
                            "host_numa_binding": numa},
                 "e2e": e2e, "gpu_launches": kpf * args.steps, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "latency": lat, "impl": "ours"}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     det.close()
 
 
@@ -352,7 +352,7 @@ def run_reference(args, rank, world):
                                            "GPU 0 driven by one host thread"},
                 "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(len(frames) * W * H),
                         "d2h_bytes_per_step": int(ref_kp * (48 + 4 * 64))}}
-        print(json.dumps(line))
+        emit(json.dumps(line))
         return
     # no reference library / no GPU: the CPU port of oracle/ on all host cores
     import oracle_lib as ol
@@ -373,10 +373,25 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{n_s} frames per step, one per OpenMP worker"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+_REAL_STDOUT = None
+
+
+def emit(text):
+    """The JSON line goes to the process's real stdout; everything else written to fd 1 meanwhile (e.g. the
+    'NCCL version' banner of the first communicator) has been sent to stderr."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
