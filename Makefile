@@ -7,7 +7,7 @@ NVFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xco
 CU_SRCS := $(CSRC)/integral.cu $(CSRC)/hessian.cu $(CSRC)/nms.cu $(CSRC)/describe.cu $(CSRC)/match.cu $(CSRC)/postmatch.cu
 OBJS    := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS)) build/ctx.o build/synth.o
 
-all: $(LIB)
+all: $(LIB) demo
 
 build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/surfb200.h
 	@mkdir -p build

@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 
 W, H = 1920, 1080
 NOCT, THRESH = 5, 4.0
-MAX_PTS = 16384
+MAX_PTS = 32768  # BASELINE configs[1]/[2]: keypoint buffer of 32768 per frame
 POOL = 16  # distinct generated frames; the batch is filled with horizontally rolled copies
 
 
@@ -46,8 +46,11 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def make_frames(n, sb):
-    pool = [sb.synth_frame(W, H, 1 + i) for i in range(min(POOL, n))]
+def make_frames(n, synth):
+    """n frames of the workload: POOL distinct synth_v1 frames (seeds 1..POOL), then horizontally rolled copies. `synth` is
+    the generator: sb.synth_frame in our arm, the bit-identical numpy port tests/synth_np.py in the reference arm (which
+    must not load the product library)."""
+    pool = [synth(W, H, 1 + i) for i in range(min(POOL, n))]
     out = np.empty((n, H, W), np.uint8)
     for f in range(n):
         out[f] = np.roll(pool[f % len(pool)], 37 * (f // len(pool)), axis=1)
@@ -99,10 +102,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def algorithmic_bytes(info, noct, n_kp, nfeat):
+def workload_config(B, world):
+    """`config` of the JSON line -- identical in both arms (the reference arm processes the same B frames per step, one
+    synchronous Surfor::detectAndCompute at a time: it has no batched entry point)."""
+    return {"workload": "BASELINE configs[1]: synth_v1 1920x1080 (seeds 1..16, rolled copies), 5 octaves x 5 layers, thresh 4, "
+                        f"upright 64-d, max_pts {MAX_PTS}; {B} distinct frames per GPU per step (configs[3] sharding)",
+            "frames_per_step_per_gpu": B, "max_pts": MAX_PTS,
+            "l2_policy": f"inputs+intermediates per step {B * (W * H + 23.6e6) / 1e6:.0f} MB > 126 MB L2",
+            "parallelism": f"frames sharded over {world} GPU(s), no collective"}
+
+
+def algorithmic_bytes(info, noct, n_kp, nfeat, w=None, h=None):
     """compulsory traffic of a staged pipeline, per frame (unpadded sizes)."""
-    b_img = W * H
-    b_int = 4 * (W + 1) * (H + 1)
+    w, h = w or W, h or H
+    b_img = w * h
+    b_int = 4 * (w + 1) * (h + 1)
     b_resp = 4 * info.max_scale * sum(info.sw[o] * info.sh[o] for o in range(noct))
     b_kp, b_desc = 48 * n_kp, 4 * nfeat * n_kp
     return {"integral": b_img + b_int, "hessian": b_int + b_resp, "nms": b_resp + b_kp,
@@ -143,7 +157,7 @@ def run_ours(args, rank, world, local_rank, dist):
     nf = det.nfeatures
     # this rank's shard of the global batch (contiguous; frames independent)
     lo, hi = sb.shard_range(B * world, world, rank)
-    frames = make_frames(B, sb) if world == 1 else np.roll(make_frames(B, sb), 11 * rank, axis=2)
+    frames = make_frames(B, sb.synth_frame) if world == 1 else np.roll(make_frames(B, sb.synth_frame), 11 * rank, axis=2)
     pitch = sb.iAlignUp(W, 128)
     h_pad = np.zeros((B, H, pitch), np.uint8)
     h_pad[:, :, :W] = frames
@@ -193,17 +207,21 @@ def run_ours(args, rank, world, local_rank, dist):
     ach = ab[names[top]] * B / (stage[top] / 1e3) / 1e9
     per_stage = {n: {"ms": float(stage[i]), "gbs": ab[n] * B / (stage[i] / 1e3) / 1e9,
                      "frac": ab[n] * B / (stage[i] / 1e3) / 1e9 / peak} for i, n in enumerate(names)}
-    # DRAM bytes of the dominant kernel per launch, from the committed ncu capture of the same batch size
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        kmap = {"describe": "describe_upright_kernel<4>", "nms": "nms_scan_tile_kernel", "hessian": "hessian_o0_kernel"}
-        if tj.get("batch") == B and names[top] in kmap:
-            traffic = tj["kernels"][kmap[names[top]]]["traffic_bytes"]
-    except Exception:
-        traffic = None
+    # DRAM bytes of the dominant kernel per launch: NOT measured in this run (ncu cannot run inside a timed bench); read from
+    # the committed `ncu --set full` capture of the same kernel at the same batch size and labelled as such
+    traffic, traffic_src = None, None
+    for tf in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            kmap = tj.get("stage_kernel", {"describe": "describe_upright_kernel<4>", "nms": "nms_scan_tile_kernel", "hessian": "hessian_o0_kernel"})
+            if tj.get("batch") == B and names[top] in kmap and kmap[names[top]] in tj["kernels"]:
+                traffic = tj["kernels"][kmap[names[top]]]["traffic_bytes"]
+                traffic_src = f"committed capture profiles/{tf} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+                break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": names[top], "achieved": ach, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": ab[names[top]] * B, "stages": per_stage,
                 "pipeline_frac": sum(ab.values()) * B / (float(stage.sum()) / 1e3) / 1e9 / peak}
 
@@ -272,6 +290,38 @@ def run_ours(args, rank, world, local_rank, dist):
         lat = {"p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)), "keypoints": data.num_pts}
         one.close()
 
+    # ---- configs[3] as written: 1 024 frames in total, STRONG-scaled over the ranks (contiguous shards, batches of B)
+    TOTAL = 1024
+    lo3, hi3 = sb.shard_range(TOTAL, world, rank)
+    n_local = hi3 - lo3
+
+    def strong_pass():
+        done = 0
+        while done < n_local:
+            nb = min(B, n_local - done)
+            det.detect_batch(d_imgs[:nb], pitch, pts[:nb], cnt[:nb], desc[:nb])
+            done += nb
+
+    strong_pass()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    strong_pass()
+    s1.record()
+    barrier()
+    tst = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tst, op=dist.ReduceOp.MAX)
+    strong = {"workload": f"BASELINE configs[3]: {TOTAL} 1080p frames in total, contiguous shards over {world} GPU(s), batches of {B}",
+              "scaling": "strong", "value": TOTAL / (float(tst.item()) / 1e3), "unit": "frames/s", "ms_total": float(tst.item()),
+              "frames_per_gpu": n_local}
+
+    # ---- configs[2] (4K) and configs[4] (stereo pairs + matching): rank 0 at N=1, extra keys of the same line
+    cfg2 = cfg4 = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        cfg2 = measure_4k(sb, torch, dev, local_rank)
+        cfg4 = measure_stereo(sb, torch, det, dev, pitch, pts, cnt, desc, B)
+
     # ---- CPU baseline (oracle port) on rank 0 at N=1 only: checker code, timed beside, never shipped
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -296,29 +346,133 @@ def run_ours(args, rank, world, local_rank, dist):
         line = {"metric": "frames/s SURF detect+describe @1080p", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-                "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: synth_v1 1920x1080, 5 octaves x 5 layers, thresh 4, upright 64-d; "
-                                       f"batch of {B} distinct frames per GPU per step (configs[3] sharding)",
-                           "frames_per_step_per_gpu": B, "keypoints_per_frame": kp_mean,
-                           "l2_policy": f"inputs+intermediates per step {B * (W * H + 23.6e6) / 1e6:.0f} MB > 126 MB L2",
-                           "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                           "host_numa_binding": numa},
+                "data": "synthetic", "config": workload_config(B, world),
+                "keypoints_per_frame": kp_mean, "host_numa_binding": numa,
                 "e2e": e2e, "gpu_launches": kpf * args.steps, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "latency": lat, "impl": "ours"}
+                "cpu_baseline": cpu, "latency": lat, "strong_scaling_configs3": strong, "configs2_4k": cfg2,
+                "configs4_stereo": cfg4, "impl": "ours"}
         emit(json.dumps(line))
     det.close()
 
 
+def measure_4k(sb, torch, dev, local_rank):
+    """BASELINE configs[2]: one synthetic 3840x2160 frame (seed 2), 5 octaves, keypoint buffer capped at MAX_PTS: p50
+    latency of the synchronous call, and per-stage achieved GB/s (algorithmic bytes of SURVEY.md 8d) on a 4-frame batch."""
+    w4, h4, B4 = 3840, 2160, 4
+    pitch = sb.iAlignUp(w4, 128)
+    buf = np.zeros((B4, h4, pitch), np.uint8)
+    for f in range(B4):
+        buf[f, :, :w4] = sb.synth_frame(w4, h4, 2 + f)
+    d = torch.from_numpy(buf).to(dev)
+    one = sb.Surfor()
+    one.init(NOCT, THRESH, False, 9, 2, True, False, 4, w4, h4, max_pts=MAX_PTS, batch=B4, device=local_rank)
+    data = sb.initSurfData(MAX_PTS, True, True, device=local_rank)
+    dd = torch.zeros((MAX_PTS, one.nfeatures), dtype=torch.float32, device=dev)
+    ts = []
+    for i in range(10 + 60):
+        torch.cuda.synchronize()
+        a = time.perf_counter()
+        one.detectAndCompute(d[0], data, (w4, h4, pitch), desc_out=dd)
+        if i >= 10:
+            ts.append((time.perf_counter() - a) * 1e3)
+    pts = torch.zeros((B4, MAX_PTS * 48), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(B4, dtype=torch.int32, device=dev)
+    desc = torch.zeros((B4, MAX_PTS, one.nfeatures), dtype=torch.float32, device=dev)
+    stage = np.zeros(4)
+    reps = 5
+    for i in range(2 + reps):
+        ms = np.array(one.detect_batch_profile(d, pitch, pts, cnt, desc))
+        if i >= 2:
+            stage += ms
+    stage /= reps
+    kp = float(cnt.cpu().numpy().mean())
+    ab = algorithmic_bytes(one.info, NOCT, kp, one.nfeatures, w4, h4)
+    peak, _ = peaks()
+    names = ["integral", "hessian", "nms", "describe"]
+    out = {"workload": f"BASELINE configs[2]: synth_v1 3840x2160 seed 2, 5 octaves, max_pts {MAX_PTS}",
+           "p50_ms": float(np.percentile(ts, 50)), "p90_ms": float(np.percentile(ts, 90)), "keypoints": int(data.num_pts),
+           "batch_for_stage_times": B4, "frames_per_s_batch": B4 / (float(stage.sum()) / 1e3),
+           "stages": {n: {"us_per_frame": 1e3 * float(stage[i]) / B4, "gbs": ab[n] * B4 / (float(stage[i]) / 1e3) / 1e9,
+                          "frac_of_hbm_peak": ab[n] * B4 / (float(stage[i]) / 1e3) / 1e9 / peak} for i, n in enumerate(names)}}
+    one.close()
+    return out
+
+
+def measure_stereo(sb, torch, det, dev, pitch, pts, cnt, desc, B):
+    """BASELINE configs[4]: 1080p stereo pairs (left seed 5000+p; right = the same texture 12 px to the side + noise):
+    detect + describe both frames, match L->R with the tcgen05 matcher on the device, accept `ambiguity < 0.8`."""
+    NP = B // 2
+    buf = np.zeros((2 * NP, H, pitch), np.uint8)
+    for p in range(NP):
+        buf[2 * p, :, :W] = sb.synth_frame(W, H, 5000 + p)
+        buf[2 * p + 1, :, :W] = sb.synth_frame(W, H, 5000 + p, 12, 2, (5000 + p) ^ 0xA5A5)
+    d = torch.from_numpy(buf).to(dev)
+
+    class View:  # SurfData-like view of one frame of the batch
+        def __init__(self, f, n):
+            self.d_data, self.num_pts, self.h_data = pts[f], n, None
+
+    def step():
+        det.detect_batch(d, pitch, pts[: 2 * NP], cnt[: 2 * NP], desc[: 2 * NP])
+        counts = cnt[: 2 * NP].cpu().numpy()  # host gather of the counts: the step's only host round trip
+        for p in range(NP):
+            det.match_async(View(2 * p, int(counts[2 * p])), View(2 * p + 1, int(counts[2 * p + 1])), desc[2 * p], desc[2 * p + 1])
+        return counts
+
+    for _ in range(3):
+        counts = step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    N = 10
+    for _ in range(N):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / N
+    # the matcher alone on pair 0 (CUDA events on the launching stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0, v1 = View(0, int(counts[0])), View(1, int(counts[1]))
+    for _ in range(3):
+        det.match_async(v0, v1, desc[0], desc[1])
+    e0.record()
+    for _ in range(20):
+        det.match_async(v0, v1, desc[0], desc[1])
+    e1.record()
+    torch.cuda.synchronize()
+    match_us = e0.elapsed_time(e1) * 1e3 / 20
+    hp = pts[0].cpu().numpy().view(sb.POINT_DTYPE)[: counts[0]]
+    tensor = None
+    try:
+        tensor = json.load(open(os.path.join(ROOT, "profiles", "r2_match.json")))
+    except Exception:
+        pass
+    n1, n2 = int(counts[0]), int(counts[1])
+    peak_tf = 1373.9
+    try:
+        peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    return {"workload": f"BASELINE configs[4]: {NP} 1080p stereo pairs per step (of 512), detect+describe both, tcgen05 match L->R, ratio 0.8",
+            "pairs_per_step": NP, "ms_per_step": dt * 1e3, "pairs_per_s": NP / dt, "keypoints_per_frame": float(counts.mean()),
+            "match_us_pair0": match_us, "match_shape": [n1, n2 - n2 % 32, 64],
+            "match_tflops_algorithmic": 2.0 * n1 * (n2 - n2 % 32) * 64 / (match_us * 1e-6) / 1e12,
+            "match_frac_of_bf16_sustained_peak": 2.0 * n1 * (n2 - n2 % 32) * 64 / (match_us * 1e-6) / 1e12 / peak_tf,
+            "match_mma_tensor_pipe_pct": None if tensor is None else tensor.get("match_mma_tensor_pipe_pct"),
+            "match_mma_tensor_pipe_source": None if tensor is None else "committed capture profiles/r2_match.json (ncu sm__pipe_tensor_cycles_active)",
+            "pair0_rows_matched": int((hp["match"] >= 0).sum()),
+            "pair0_rows_with_ambiguity_lt_0_8": int(((hp["ambiguity"] < 0.8) & (hp["match"] >= 0)).sum())}
+
+
 def run_reference(args, rank, world):
-    """The reference's own implementation on the same workload, rank 0 only."""
+    """The reference's own implementation on the same workload, rank 0 only. This arm never imports the product package:
+    the frames come from the numpy port of the generator (tests/synth_np.py, bit-identical), the timed path is the
+    unmodified surfd.cu + surf.cpp of oracle/_ref driven through Surfor::detectAndCompute."""
     if rank != 0:
         return
-    import cuda_surf_b200 as sb
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth_np
     B = args.batch
-    frames = make_frames(min(B, POOL), sb)
-    cfg = {"workload": "BASELINE configs[1]: synth_v1 1920x1080, 5 octaves x 5 layers, thresh 4, upright 64-d",
-           "frames_per_step": len(frames)}
+    frames = make_frames(B, synth_np.synth_frame)
+    cfg = workload_config(B, world)
     import ref_lib
     have_gpu = False
     if ref_lib.available():
@@ -347,7 +501,7 @@ def run_reference(args, rank, world):
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic", "config": cfg,
                 "impl": "reference",
                 "cpu_baseline": {"value": value, "unit": "frames/s", "cores": 1, "kind": "reference",
-                                 "sample": f"{len(frames)} frames per step through Surfor::detectAndCompute of the unmodified "
+                                 "sample": f"{len(frames)} frames per step, one synchronous call each, through Surfor::detectAndCompute of the unmodified "
                                            "reference built for sm_100a (oracle/_ref); it is a CUDA program, so it runs on "
                                            "GPU 0 driven by one host thread"},
                 "e2e": {"value": e2e_v, "unit": "frames/s", "h2d_bytes_per_step": int(len(frames) * W * H),
@@ -399,6 +553,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="frames per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] (4K) and configs[4] (stereo) legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -32,13 +32,14 @@ class SurfError(RuntimeError):
 class SbParams(C.Structure):
     _fields_ = [("noctaves", C.c_int), ("thresh", C.c_float), ("doubled", C.c_int), ("init_mask_size", C.c_int),
                 ("sampling_step", C.c_int), ("upright", C.c_int), ("extend", C.c_int), ("desc_wsz", C.c_int),
-                ("width", C.c_int), ("height", C.c_int), ("max_pts", C.c_int), ("batch", C.c_int), ("device", C.c_int)]
+                ("width", C.c_int), ("height", C.c_int), ("max_pts", C.c_int), ("batch", C.c_int), ("device", C.c_int),
+                ("fresh_desc", C.c_int)]
 
 
 class SbInfo(C.Structure):
     _fields_ = [("max_scale", C.c_int), ("nfeatures", C.c_int), ("iw", C.c_int), ("ih", C.c_int), ("ipitch", C.c_int),
                 ("sw", C.c_int * 8), ("sh", C.c_int * 8), ("sp", C.c_int * 8), ("resp_floats", C.c_longlong),
-                ("kernels_per_frame", C.c_int)]
+                ("kernels_per_frame", C.c_int), ("cand_capacity", C.c_int)]
 
 
 def build_library(force=False):

@@ -52,6 +52,7 @@ struct PipeP {
     int doubled;              // 1: w, h, iw, ih describe the 2x up-sampled frame (surf.cpp:69-72, 234-235)
     int max_pts;
     int hess_tiles, nms_tiles;  // total linear tiles per frame
+    int nms_cells;              // 2x2x2 NMS cells per frame = capacity of the candidate queue (it cannot overflow)
     OctaveP oct[kMaxOctave];
     // exp tables of Surfor::initLut (surf.cpp:358-371) and the angle bins of surf.cpp:83-90
     float lut1[83];

@@ -8,7 +8,8 @@
 // The reference re-derives and re-uploads all of this per octave per frame; here it is derived
 // once in sb_create into a PipeP block that every kernel receives by value, scratch is allocated
 // and zeroed once (valid regions are fully rewritten each frame, so the per-frame 23 MB memsets of
-// surf.cpp:345-349 are gone), and a frame is 5 kernel launches with no host round trip.
+// surf.cpp:345-349 are gone), and a frame is sb_info.kernels_per_frame launches (8 for the default configuration)
+// with no host round trip.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -24,8 +25,8 @@
 
 using namespace sb;
 
-// one batch in flight on the host-buffer path: staging buffers, events and chunk schedule. Three sets: while batch k
-// downloads, batch k+1 computes and batch k+2 uploads.
+// one batch in flight on the host-buffer path: staging buffers, events and chunk schedule. THREE sets (kHostSets): while
+// batch k downloads, batch k+1 computes and batch k+2 uploads.
 constexpr int kHostSets = 3;
 struct HostJob {
     uint8_t* d_img = nullptr;
@@ -65,9 +66,11 @@ struct sb_ctx {
     sb_point* h_pts = nullptr;        // pinned, max_pts
     // sb_detect_and_compute replays one captured CUDA graph per (image, points, descriptor) pointer set: the eight launches,
     // the counter memset and the two result copies of a frame go down as one submission
-    struct FrameGraph { const void* img; int pitch; void* pts; void* desc; int spec; cudaGraphExec_t exec; };
+    struct FrameGraph { const void* img; int pitch; void* pts; void* desc; int spec; cudaGraphExec_t exec; unsigned long long used; };
     std::vector<FrameGraph> graphs;
-    bool graphs_ok = true;
+    unsigned long long graph_clock = 0;
+    int graph_failures = 0;
+    float* d_desc_own = nullptr;      // fresh_desc: descriptors of the synchronous call before they are copied out
     MatchScratch match_ws;
     sb_point* h_match = nullptr;      // pinned staging of sb_match's host copy
     size_t h_match_cap = 0;
@@ -125,6 +128,7 @@ static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
     int sw = (P.iw - 1) / P.sampling, sh = (P.ih - 1) / P.sampling;
     long long roff = 0;
     int hess_tiles = 0, nms_tiles = 0;
+    long long nms_cells = 0;
     // octave schedule, surf.cpp:240-294 + surfd.cu:2844-2865
     int mask = P.init_lobe - 2, octave = 1, s = 0, border1 = 0;
     int borders[kMaxScale] = {0};
@@ -159,6 +163,9 @@ static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
         for (int k = 1; k < P.max_scale - 1; k += 2) {
             q.mb[q.nmb] = borders[k + 1] + 1;
             if (q.mb[q.nmb] < mbmin) mbmin = q.mb[q.nmb];
+            // cells of this cell layer: rows i = mb + 2 yc < sh - mb, columns likewise (surfd.cu:690-697)
+            const int cwz = (sw - 2 * q.mb[q.nmb] + 1) / 2, chz = (sh - 2 * q.mb[q.nmb] + 1) / 2;
+            if (cwz > 0 && chz > 0) nms_cells += (long long)cwz * chz;
             q.nmb++;
         }
         q.hess_tile0 = hess_tiles; q.hess_tx = (sw + 31) / 32; q.hess_ty = (sh + kHessRows - 1) / kHessRows;
@@ -178,6 +185,7 @@ static int build_pipe(const sb_params& p, PipeP& P, std::string& why) {
     P.rstride = roff;
     P.hess_tiles = hess_tiles;
     P.nms_tiles = nms_tiles;
+    P.nms_cells = (int)std::min<long long>(std::max<long long>(nms_cells, 1), 1LL << 30);
     // tables: surf.cpp:358-371 (expf on the host, as the reference) and surf.cpp:83-90
     for (int n = 0; n < 83; n++) P.lut1[n] = expf(-(n + 0.5f) / 12.5f);
     for (int n = 0; n < 40; n++) P.lut2[n] = expf(-(n + 0.5f) / 8.f);
@@ -193,7 +201,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_integral); cudaFree(ctx->d_integral_ph); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
-    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_work); 
+    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_work); cudaFree(ctx->d_desc_own);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     free_match_scratch(ctx->match_ws);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -234,13 +242,20 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     c->prm = *params; c->P = P; c->device = params->device; c->sm_count = prop.multiProcessorCount;
     const int B = params->batch;
     const size_t isz = sizeof(int) * (size_t)P.istride * B;
-    const size_t rsz = sizeof(float) * (size_t)P.rstride * B;
+    // + one row and one float past the last slot: with sampling_step >= 11 the lagged border of the reference's move rule
+    // (surfd.cu:804-808) is 1, so the quadratic fit can read row `sh` of the last layer of the last slot
+    const size_t rsz = sizeof(float) * ((size_t)P.rstride * B + (size_t)P.oct[0].sp + 1);
     const size_t tsz = sizeof(int) * (size_t)P.nbands * P.nchunks * 256 * B;
     const size_t rowsz = sizeof(int) * (size_t)P.nbands * 32 * P.nchunks * B;
     const size_t ttsz = sizeof(int) * (size_t)P.nbands * P.nchunks * B;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // A BLOCKING stream (cudaStreamDefault): it orders itself after everything the caller has already put on the legacy
+    // default stream and the default stream orders itself after it, which is the contract of the reference (all of its
+    // work runs on stream 0, so a frame produced by an earlier kernel of the caller is complete before it is read, and
+    // a fill of the result buffers cannot land after the results). The synchronous entry points run here; the *_async
+    // ones use the caller's stream as given.
+    ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault));
     ok(cudaMalloc((void**)&c->d_integral, isz));
     ok(cudaMalloc((void**)&c->d_integral_ph, isz));
     ok(cudaMalloc((void**)&c->d_resp, rsz));
@@ -248,9 +263,10 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     ok(cudaMalloc((void**)&c->d_rowsum, rowsz));
     ok(cudaMalloc((void**)&c->d_tilesum, ttsz));
     ok(cudaMalloc((void**)&c->d_counts, sizeof(int) * B));
-    // candidates that survive the 3x3x3 test are ~1.1x the final keypoints; 4x max_pts never overflows in practice and
-    // an overflow only drops candidates (the reference's cap is racy as well)
-    c->cand_cap = (int)std::min<long long>(4LL * P.max_pts, 1LL << 24);
+    // one queue slot per 2x2x2 NMS cell of the frame: a cell yields at most one candidate, so the queue cannot overflow
+    // whatever the threshold (1.3 MB per 1080p frame; with a capacity tied to max_pts a low threshold silently dropped
+    // candidates). The keypoint append itself stays bounded by max_pts, like the reference's (surf.cpp:302-303).
+    c->cand_cap = P.nms_cells;
     ok(cudaMalloc((void**)&c->d_cand, sizeof(unsigned) * (size_t)c->cand_cap * B));
     ok(cudaMalloc((void**)&c->d_cand_count, sizeof(int) * B));
     ok(cudaMalloc((void**)&c->d_work, sizeof(int) * 2 * B));  // [0, B): descriptor pass, [B, 2B): orientation pass
@@ -295,6 +311,7 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
     // (the octave-0 shared-memory Hessian kernel exists for the reference's default geometry only, hessian.cu)
     const bool fast0 = P.sampling == 2 && P.init_lobe == 3 && P.max_scale == 5;
     const int nhess = fast0 ? (P.noctaves > 1 ? 2 : 1) : 1;
+    info->cand_capacity = ctx->cand_cap;
     info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + nhess + 2 /*nms scan, refine*/ + 1 /*clamp*/ + (P.upright ? 1 : 2);
     return SB_OK;
 }
@@ -344,8 +361,14 @@ extern "C" int sb_detect_batch_profile(sb_ctx* ctx, const uint8_t* d_images, siz
         return fail(ctx, SB_ERR_INVALID, "sb_detect_batch_profile: bad argument");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    cudaEvent_t ev[5];
-    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&ev[i]));
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 5; i++) {
+        const cudaError_t ce = cudaEventCreate(&ev[i]);
+        if (ce != cudaSuccess) {
+            for (int k = 0; k < i; k++) cudaEventDestroy(ev[k]);
+            return fail(ctx, SB_ERR_CUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(ce));
+        }
+    }
     int rc = enqueue_frames(ctx, d_images, image_stride, pitch, nframes, d_points, d_counts, d_desc, st, ev);
     if (rc == SB_OK) {
         cudaError_t e = cudaEventSynchronize(ev[4]);
@@ -382,15 +405,24 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
     if (pitch < w) return fail(ctx, SB_ERR_INVALID, "sb_detect_and_compute: pitch < width");
     CU(cudaSetDevice(ctx->device));
     float* d_desc = nullptr;
+    float* fresh = nullptr;  // fresh_desc: the buffer handed to the caller; the kernels write the context's own buffer
     if (want_desc && d_desc_addr) {
-        if (!*d_desc_addr) {
-            // like the reference (surfd.cu:3264) the callee allocates and the caller cudaFree's; unlike
-            // it, a non-NULL *d_desc_addr (the buffer of the previous call, main.cpp:241-245) is reused
-            float* buf = nullptr;
-            CU(cudaMalloc((void**)&buf, sizeof(float) * (size_t)P.max_pts * P.nfeatures));
-            *d_desc_addr = buf;
+        if (ctx->prm.fresh_desc) {
+            // the reference's contract (surfd.cu:3262-3266): a new buffer every call, *d_desc_addr overwritten, the caller
+            // frees each of them. The frame is computed into a context-owned buffer (so the captured graph is reused) and
+            // the num_pts rows are copied into the fresh allocation.
+            if (!ctx->d_desc_own) CU(cudaMalloc((void**)&ctx->d_desc_own, sizeof(float) * (size_t)P.max_pts * P.nfeatures));
+            d_desc = ctx->d_desc_own;
+        } else {
+            if (!*d_desc_addr) {
+                // the callee allocates and the caller cudaFree's, like the reference; a non-NULL *d_desc_addr (the buffer
+                // of the previous call, main.cpp:241-245) is reused instead of leaked
+                float* buf = nullptr;
+                CU(cudaMalloc((void**)&buf, sizeof(float) * (size_t)P.max_pts * P.nfeatures));
+                *d_desc_addr = buf;
+            }
+            d_desc = *d_desc_addr;
         }
-        d_desc = *d_desc_addr;
     }
     cudaStream_t st = ctx->stream;
     // One host round trip instead of two: the first kSpec points travel with the count (5 k keypoints are typical at
@@ -404,13 +436,17 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
         if (spec > 0) CU(cudaMemcpyAsync(ctx->h_pts, d_points, sizeof(sb_point) * (size_t)spec, cudaMemcpyDeviceToHost, st));
         return SB_OK;
     };
+    // One captured graph per (image, points, descriptor) pointer set, at most kMaxGraphs of them, least recently used
+    // evicted (a caller that passes a new descriptor or image pointer every frame then pays a capture per call, but
+    // never runs out of cache or keeps stale executables alive). A pointer set whose capture failed is launched plainly;
+    // three failures switch graphs off for the context.
+    constexpr size_t kMaxGraphs = 16;
     bool launched = false;
-    if (ctx->graphs_ok) {
+    if (ctx->graph_failures < 3) {
         sb_ctx::FrameGraph* hit = nullptr;
         for (auto& g : ctx->graphs)
             if (g.img == d_image && g.pitch == pitch && g.pts == d_points && g.desc == d_desc && g.spec == spec) { hit = &g; break; }
-        if (!hit && ctx->graphs.size() < 16) {
-            // capture this pointer set once (the demo loop of main.cpp:239-245 alternates between two)
+        if (!hit) {
             cudaGraph_t graph = nullptr;
             cudaGraphExec_t exec = nullptr;
             bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
@@ -421,14 +457,22 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
             if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
             if (graph) cudaGraphDestroy(graph);
             if (ok) {
-                ctx->graphs.push_back({d_image, pitch, d_points, d_desc, spec, exec});
+                if (ctx->graphs.size() >= kMaxGraphs) {
+                    size_t lru = 0;
+                    for (size_t k = 1; k < ctx->graphs.size(); k++)
+                        if (ctx->graphs[k].used < ctx->graphs[lru].used) lru = k;
+                    cudaGraphExecDestroy(ctx->graphs[lru].exec);
+                    ctx->graphs.erase(ctx->graphs.begin() + lru);
+                }
+                ctx->graphs.push_back({d_image, pitch, d_points, d_desc, spec, exec, 0});
                 hit = &ctx->graphs.back();
             } else {
-                cudaGetLastError();      // clear; fall back to plain launches for good
-                ctx->graphs_ok = false;
+                cudaGetLastError();  // clear; this call goes down as plain launches
+                ctx->graph_failures++;
             }
         }
-        if (hit && ctx->graphs_ok) {
+        if (hit) {
+            hit->used = ++ctx->graph_clock;
             CU(cudaGraphLaunch(hit->exec, st));
             launched = true;
         }
@@ -440,6 +484,13 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
     CU(cudaStreamSynchronize(st));
     const int n = ctx->h_counts[0];
     *num_pts = n;
+    if (want_desc && d_desc_addr && ctx->prm.fresh_desc) {
+        // surfd.cu:3262-3264: num_pts * nfeatures floats, a new allocation per call (one float when there are no keypoints)
+        CU(cudaMalloc((void**)&fresh, sizeof(float) * std::max<size_t>((size_t)n * P.nfeatures, 1)));
+        if (n > 0) CU(cudaMemcpyAsync(fresh, d_desc, sizeof(float) * (size_t)n * P.nfeatures, cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
+        *d_desc_addr = fresh;
+    }
     if (h_points && n > 0) {
         if (n > spec) {
             CU(cudaMemcpyAsync(ctx->h_pts + spec, d_points + spec, sizeof(sb_point) * (size_t)(n - spec), cudaMemcpyDeviceToHost, st));
@@ -453,7 +504,7 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
     return SB_OK;
 }
 
-// ---- host-buffer path: submit / wait over two staging sets
+// ---- host-buffer path: submit / wait over three staging sets (kHostSets)
 //
 // Pipelined ingest / compute / egress. A batch is cut into chunks; chunk k's frames go up on the ingest stream, its
 // kernels run on a compute stream behind an event, and as soon as its keypoint counts are visible on the host the
@@ -529,6 +580,7 @@ extern "C" int sb_submit_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
         }
     }
     const size_t pstride = (size_t)P.max_pts, dstride_f = (size_t)P.max_pts * P.nfeatures;
+    const int rc_enq = [&]() -> int {
     for (int k = 0; k < nchunks; k++) {
         const int f0 = J.first[k], nf = J.first[k + 1] - f0;
         cudaStream_t st = (k & 1) ? ctx->stream2 : ctx->stream;
@@ -549,6 +601,15 @@ extern "C" int sb_submit_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nf
     }
     CU(cudaEventRecord(J.ev_end[0], ctx->stream));
     CU(cudaEventRecord(J.ev_end[1], ctx->stream2));
+    return SB_OK;
+    }();
+    if (rc_enq != SB_OK) {
+        // some chunks may already be enqueued: let them finish, then forget this batch (its schedule must not be taken for
+        // the "previous batch" of the next submit, and its staging set is free again)
+        cudaStreamSynchronize(ctx->s_h2d); cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream2);
+        J.submitted = false; J.active = false; J.nframes = 0; J.first.clear();
+        return rc_enq;
+    }
     J.nframes = nframes; J.want_desc = want_desc != 0; J.active = true; J.submitted = true;
     *ticket = set;
     ctx->next_set = (set + 1) % kHostSets;
@@ -565,7 +626,15 @@ extern "C" int sb_wait_batch_host(sb_ctx* ctx, int ticket, sb_point* h_points, i
     CU(cudaSetDevice(ctx->device));
     const size_t pstride = (size_t)P.max_pts, dstride_f = (size_t)P.max_pts * P.nfeatures;
     const int nchunks = (int)J.first.size() - 1;
-    J.active = false;
+    // the set is handed back only when its kernels and copies are known to be complete: a failing call below drains the
+    // streams first (WAITFAIL), so a later submit cannot reuse staging buffers that are still being written
+    struct Guard {
+        sb_ctx* c; HostJob& j; bool ok = false;
+        ~Guard() {
+            if (!ok) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->s_d2h); }
+            j.active = false;
+        }
+    } guard{ctx, J};
     for (int k = 0; k < nchunks; k++) {
         const int f0 = J.first[k], nf = J.first[k + 1] - f0;
         CU(cudaEventSynchronize(J.ev_done[k]));  // counts of chunk k are on the host; later chunks keep running
@@ -586,6 +655,7 @@ extern "C" int sb_wait_batch_host(sb_ctx* ctx, int ticket, sb_point* h_points, i
                                  sizeof(float) * (size_t)nmax * P.nfeatures, nf, cudaMemcpyDeviceToHost, ctx->s_d2h));
     }
     CU(cudaStreamSynchronize(ctx->s_d2h));
+    guard.ok = true;
     return SB_OK;
 }
 

@@ -71,10 +71,10 @@ class Surfor:
     # Surfor::init. The keyword-only arguments are capacities the reference takes from SurfData or has
     # no notion of (keypoints per frame, frames per batched call, device ordinal).
     def init(self, noctaves, thresh=0.2, doubled=False, init_mask_size=9, sampling_step=2, upright=False, extend=False,
-             desc_wsz=4, width=-1, height=-1, *, max_pts=10000, batch=1, device=0):
+             desc_wsz=4, width=-1, height=-1, *, max_pts=10000, batch=1, device=0, fresh_desc=False):
         self.close()
         p = B.SbParams(noctaves, thresh, int(doubled), init_mask_size, sampling_step, int(upright), int(extend),
-                       desc_wsz, width, height, max_pts, batch, device)
+                       desc_wsz, width, height, max_pts, batch, device, int(fresh_desc))
         ctx = C.c_void_p(None)
         B.check(B.lib().sb_create(C.byref(ctx), C.byref(p)), None)
         self._ctx = ctx
@@ -100,13 +100,18 @@ class Surfor:
         hp = result.h_data.ctypes.data if result.h_data is not None else None
         addr = None
         if desc:
-            if desc_out is None:
-                desc_out = torch.empty((result.max_pts, self.nfeatures), dtype=torch.float32, device=image.device)
-            addr = C.c_void_p(desc_out.data_ptr())
+            if self.params.fresh_desc:
+                addr = C.c_void_p(None)  # the library allocates (cudaMalloc) a new buffer per call: see detect_fresh()
+            else:
+                if desc_out is None:
+                    desc_out = torch.empty((result.max_pts, self.nfeatures), dtype=torch.float32, device=image.device)
+                addr = C.c_void_p(desc_out.data_ptr())
         rc = B.lib().sb_detect_and_compute(self._ctx, image.data_ptr(), w, h, pitch, result.d_data.data_ptr(), hp,
                                            result.max_pts, C.byref(n), C.byref(addr) if desc else None, int(desc))
         B.check(rc, self._ctx)
         result.num_pts = n.value
+        if desc and self.params.fresh_desc:
+            return addr.value  # raw device pointer owned by the caller (cudaFree), as with the reference
         return desc_out if desc else None
 
     # Surfor::match(data1, data2, features1, features2)
@@ -130,7 +135,7 @@ class Surfor:
         cross-check (data2 must then hold the reverse match). Returns a numpy array of PAIR_DTYPE in row order."""
         import torch
         n1 = data1.num_pts
-        pairs = torch.zeros((max(n1, 1), 16), dtype=torch.uint8, device=data1.d_data.device)
+        pairs = torch.empty((max(n1, 1), 16), dtype=torch.uint8, device=data1.d_data.device)
         host = np.zeros(max(n1, 1), B.PAIR_DTYPE)
         n = C.c_int(0)
         flags = (B.FILTER_LAPLACE if laplace else 0) | (B.FILTER_CROSS if cross else 0)
@@ -172,8 +177,8 @@ class Surfor:
         B.check(rc, self._ctx)
 
     def submit_batch_host(self, frames, want_desc=True):
-        """First half of detect_batch_host: uploads + kernels of a batch are enqueued, a ticket comes back. At most two
-        batches may be outstanding; `frames` must stay alive until the ticket has been waited for."""
+        """First half of detect_batch_host: uploads + kernels of a batch are enqueued, a ticket comes back. At most THREE
+        batches may be outstanding (three staging sets); `frames` must stay alive until the ticket has been waited for."""
         t = C.c_int(-1)
         rc = B.lib().sb_submit_batch_host(self._ctx, _hptr(frames), frames.shape[0], int(want_desc), C.byref(t))
         B.check(rc, self._ctx)

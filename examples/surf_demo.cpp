@@ -3,6 +3,9 @@
 // counts and times. Written against include/compat/surf.h, i.e. the reference's own surf.h interface.
 //
 //   surf_demo [device] [left.pgm right.pgm]        (no files: two 1280x960 synth_v1 frames 12 px apart)
+// Environment: SURFB200_FRESH_DESC=1 keeps the reference's descriptor-buffer contract (a new cudaMalloc per call,
+// surfd.cu:3262-3266); SURF_DEMO_REPEATS=n overrides the 100 repetitions of main.cpp:239-251. The last lines are
+// machine-readable (`key=value`) for tests/test_demo_gpu.py.
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -68,8 +71,18 @@ int main(int argc, char** argv) {
     std::unique_ptr<surf::Surfor> detector(new surf::Surfor);
     detector->init(octaves, thres, doubleImageSize, initLobe * 3, samplingStep, upright, extended, indexSize, w, h);
 
-    const int nrepeats = 100;
+    const int nrepeats = std::getenv("SURF_DEMO_REPEATS") ? std::max(1, std::atoi(std::getenv("SURF_DEMO_REPEATS"))) : 100;
     detector->detectAndCompute(img1, d1, whp, &desc1, true);  // context creation outside the timed loop
+    // descriptor-buffer contract: what happens to the first pointer when the same variable is passed again
+    float* first_ptr = desc1;
+    std::vector<float> first_copy((size_t)d1.num_pts * 64);
+    CHECK(cudaMemcpy(first_copy.data(), first_ptr, first_copy.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    detector->detectAndCompute(img2, d2, whp, &desc1, true);  // a different frame through the same variable
+    const bool fresh = desc1 != first_ptr;
+    std::vector<float> again(first_copy.size());
+    CHECK(cudaMemcpy(again.data(), first_ptr, again.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    const bool first_intact = again == first_copy;
+    if (fresh) { CHECK(cudaFree(first_ptr)); }
     const float t1 = timer.read();
     for (int i = 0; i < nrepeats; i++) {
         detector->detectAndCompute(img1, d1, whp, &desc1, true);
@@ -91,6 +104,13 @@ int main(int argc, char** argv) {
                     d1.h_data[0].y, d1.h_data[0].scale, d1.h_data[0].strength, d1.h_data[0].laplace, d1.h_data[0].match,
                     d1.h_data[0].score);
 
+    std::printf("features1=%d\nfeatures2=%d\ngood=%d\ndesc_fresh=%d\nfirst_desc_intact=%d\n", d1.num_pts, d2.num_pts, good,
+                fresh ? 1 : 0, first_intact ? 1 : 0);
+    // per-row match results of the left image for the parity test: index and score
+    if (const char* dump = std::getenv("SURF_DEMO_DUMP")) {
+        std::ofstream o(dump, std::ios::binary);
+        o.write((const char*)d1.h_data, sizeof(surf::SurfPoint) * (size_t)d1.num_pts);
+    }
     surf::freeSurfData(d1);
     surf::freeSurfData(d2);
     CHECK(cudaFree(img1));

@@ -43,6 +43,16 @@ public:
         prm_.noctaves = _noctaves; prm_.thresh = _thresh; prm_.doubled = _doubled; prm_.init_mask_size = _init_mask_size;
         prm_.sampling_step = _sampling_step; prm_.upright = _upright; prm_.extend = _extend; prm_.desc_wsz = _desc_wsz;
         prm_.width = _width; prm_.height = _height; prm_.batch = 1;
+        // Descriptor buffer ownership. Default: *desc_addr is allocated on first use and REUSED when the caller passes
+        // it again (main.cpp:241-245 does; the reference leaks 199 buffers there). A caller that relies on the
+        // reference's literal contract -- a fresh cudaMalloc per call, the previous pointer left alone
+        // (surfd.cu:3262-3266) -- builds with -DSURFB200_FRESH_DESC=1 or runs with SURFB200_FRESH_DESC=1 in the environment.
+#ifdef SURFB200_FRESH_DESC
+        prm_.fresh_desc = SURFB200_FRESH_DESC;
+#else
+        prm_.fresh_desc = 0;
+#endif
+        if (const char* e = std::getenv("SURFB200_FRESH_DESC")) prm_.fresh_desc = std::atoi(e) != 0;
         CHECK(cudaGetDevice(&prm_.device));
         if (ctx_) { sb_destroy(ctx_); ctx_ = NULL; }
     }

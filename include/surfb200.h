@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SB_VERSION 100
+#define SB_VERSION 200
 
 typedef enum {
     SB_OK = 0,
@@ -59,6 +59,9 @@ typedef struct sb_params {
     int max_pts;        /* keypoint capacity per frame (SurfData.max_pts)       */
     int batch;          /* frames per batched call (scratch capacity), >= 1     */
     int device;         /* CUDA device ordinal                                  */
+    int fresh_desc;     /* 1: sb_detect_and_compute cudaMalloc's a NEW descriptor buffer of num_pts*nfeatures floats on
+                           every call and overwrites *d_desc_addr, exactly as cuDescribe does (surfd.cu:3262-3266; the
+                           caller frees each). 0 (default): a non-NULL *d_desc_addr is reused.                        */
 } sb_params;
 
 /* Derived geometry (surf.cpp:374-390), for callers that size buffers. */
@@ -68,6 +71,8 @@ typedef struct sb_info {
     int sw[8], sh[8], sp[8];   /* per-octave response dims and pitch             */
     long long resp_floats;     /* tight floats per frame: sum max_scale*sw*sh    */
     int kernels_per_frame;     /* launches per detect+describe pass              */
+    int cand_capacity;         /* slots of the NMS candidate queue per frame = number of 2x2x2 cells: a cell yields at most
+                                  one candidate, so the queue cannot overflow at any threshold                           */
 } sb_info;
 
 typedef struct sb_ctx sb_ctx;
@@ -80,6 +85,13 @@ void sb_destroy(sb_ctx* ctx);
 const char* sb_last_error(const sb_ctx* ctx);
 int sb_get_info(const sb_ctx* ctx, sb_info* info);
 
+/* Stream contract. The synchronous entry points (sb_detect_and_compute, sb_match, sb_match_filter, sb_describe, the
+ * host-buffer batch calls) run on a context-owned BLOCKING stream: like the reference, whose work all runs on the legacy
+ * default stream, they are ordered after everything the caller has enqueued on stream 0 (the default stream of torch, of
+ * cudaMemcpy, of kernels launched without a stream) and stream-0 work issued afterwards is ordered after them. A caller
+ * that produces inputs on another (non-blocking) stream must synchronise that stream first, or use the *_async entry
+ * points, which run on the stream they are given and nowhere else.                                                    */
+
 /* Surfor::detectAndCompute (surf.h:36, surf.cpp:205-355). Synchronous.
  *   d_image   device u8, row pitch `pitch` bytes, w x h must equal the context's size
  *   d_points  device array of max_pts points (SurfData.d_data); all detector fields written
@@ -89,7 +101,8 @@ int sb_get_info(const sb_ctx* ctx, sb_info* info);
  *             max_pts*nfeatures floats is cudaMalloc'ed and stored there (caller cudaFree's it,
  *             as main.cpp:275-282 does). *d_desc_addr != NULL: that buffer (>= max_pts*nfeatures
  *             floats) is reused -- the reference allocates a new one every call and leaks the
- *             old (surfd.cu:3264).
+ *             old (surfd.cu:3264). With sb_params.fresh_desc = 1 the reference's behaviour is kept
+ *             literally: *d_desc_addr is overwritten with a new num_pts*nfeatures allocation per call.
  *   want_desc 0 -> detection only (the `desc` flag).                                          */
 int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w, int h, int pitch, sb_point* d_points,
                           sb_point* h_points, int max_pts, int* num_pts, float** d_desc_addr, int want_desc);
@@ -131,7 +144,7 @@ int sb_detect_batch_async(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
 int sb_detect_batch_host(sb_ctx* ctx, const uint8_t* h_images, int nframes, sb_point* h_points, int* h_counts,
                          float* h_desc);
 /* The same in two halves, for a caller that streams batches: sb_submit_batch_host enqueues the uploads and kernels of a
- * batch and returns a ticket (at most three outstanding); sb_wait_batch_host downloads that batch's counts, points and
+ * batch and returns a ticket (at most THREE outstanding); sb_wait_batch_host downloads that batch's counts, points and
  * descriptors and returns when they are in the caller's buffers. With two batches submitted ahead, batch k downloads
  * while batch k+1 computes and batch k+2 uploads. h_images must stay valid until the ticket has been waited for.
  * h_points [nframes][max_pts], h_desc [nframes][max_pts][nfeatures]: entries [0, h_counts[f]) of frame f are results;

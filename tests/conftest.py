@@ -29,3 +29,41 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+# ---- parity report: every disagreement the GPU parity tests see (keypoints unmatched either way, descriptor rows over
+# 1e-4, match rows that differ) is collected here and written at the end of a GPU session to gpurun_out/ (which travels
+# back from the GPU box) and to profiles/parity_report.json (committed copy).
+class _ParityReport:
+    def __init__(self):
+        self.entries = {}
+
+    def add(self, test, **kw):
+        self.entries.setdefault(test, []).append(kw)
+
+
+PARITY = _ParityReport()
+
+
+@pytest.fixture
+def report(request):
+    name = request.node.name
+
+    def add(**kw):
+        PARITY.add(name, **kw)
+    return add
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not PARITY.entries:
+        return
+    import json
+    doc = {"what": "disagreements seen by `pytest -m gpu` (tests/test_parity_gpu.py, tests/test_demo_gpu.py); empty lists = none",
+           "exitstatus": int(exitstatus), "tests": PARITY.entries}
+    for d in ("gpurun_out", "profiles"):
+        try:
+            os.makedirs(os.path.join(ROOT, d), exist_ok=True)
+            with open(os.path.join(ROOT, d, "parity_report.json"), "w") as f:
+                json.dump(doc, f, indent=1, default=float)
+        except OSError:
+            pass

@@ -58,3 +58,25 @@ def describe_misses(miss, thresh):
         lines.append(f"  x={p['x']:.3f} y={p['y']:.3f} scale={p['scale']:.3f} strength={p['strength']:.4f}"
                      f"{'  (threshold boundary)' if abs(p['strength'] - thresh) < 0.02 * thresh else ''}")
     return "\n".join(lines)
+
+
+def point_rows(pts, limit=40):
+    """keypoints as plain dicts for the parity report"""
+    return [{"x": float(p["x"]), "y": float(p["y"]), "scale": float(p["scale"]), "strength": float(p["strength"])}
+            for p in pts[:limit]]
+
+
+def parity_entry(what, ref_pts, got_pts, ok, idx, miss_r, miss_g, l2=None, thresh=4.0, extra=None):
+    """One record of the parity report: counts, unmatched keypoints both ways (flagged when their strength is within
+    2 % of the threshold), descriptor rows whose L2 distance exceeds 1e-4 (listed) and the maximum."""
+    e = {"case": what, "n_ref": int(len(ref_pts)), "n_ours": int(len(got_pts)), "matched": int(ok.sum()),
+         "ref_only": [dict(r, threshold_boundary=bool(abs(r["strength"] - thresh) < 0.02 * thresh)) for r in point_rows(miss_r)],
+         "ours_only": [dict(r, threshold_boundary=bool(abs(r["strength"] - thresh) < 0.02 * thresh)) for r in point_rows(miss_g)]}
+    if l2 is not None and len(l2):
+        over = np.nonzero(l2 > 1e-4)[0]
+        e["desc_l2_max"] = float(l2.max())
+        e["desc_rows_over_1e-4"] = [{"ref_row": int(np.nonzero(ok)[0][i]), "l2": float(l2[i])} for i in over[:40]]
+        e["desc_rows_over_1e-4_count"] = int(len(over))
+    if extra:
+        e.update(extra)
+    return e

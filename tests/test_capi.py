@@ -31,7 +31,7 @@ def test_point_layout_is_surfpoint():
     # surf_structures.h:7-31 -- 12 four-byte fields, 48 bytes, match fields start at `score`
     assert B.POINT_DTYPE.itemsize == 48
     assert B.POINT_DTYPE.fields["score"][1] == 28 and B.POINT_DTYPE.fields["ambiguity"][1] == 44
-    assert C.sizeof(B.SbParams) == 13 * 4
+    assert C.sizeof(B.SbParams) == 14 * 4  # 13 arguments of round 1 + fresh_desc
 
 
 def _has_gpu():

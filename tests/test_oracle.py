@@ -197,3 +197,12 @@ def test_doubled_detect_is_consistent_with_plain_detect_on_the_2x_frame():
     assert np.allclose(np.sort(pp["x"]) * 0.5, np.sort(pd["x"]), atol=1e-5)
     assert np.allclose(np.sort(pp["scale"]) * 0.5, np.sort(pd["scale"]), atol=1e-5)
     assert np.allclose(np.linalg.norm(dd, axis=1), 1.0, atol=1e-4)
+
+
+def test_synth_numpy_port_equals_library_generator():
+    """tests/synth_np.py (used by the reference arm of bench.py, which must not load the product library) is
+    bit-identical to sb_synth_frame (host code of the library; no GPU needed)."""
+    import cuda_surf_b200 as sb
+    import synth_np
+    for w, h, seed, extra in [(320, 240, 3, ()), (333, 251, 4, (12, 2, 99)), (640, 480, 5000, (12, 2, 5000 ^ 0xA5A5))]:
+        assert np.array_equal(synth_np.synth_frame(w, h, seed, *extra), sb.synth_frame(w, h, seed, *extra))

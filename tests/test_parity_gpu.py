@@ -13,9 +13,17 @@ import pytest
 
 import oracle_lib as ol
 import ref_lib
-from helpers import describe_misses, keypoint_parity, load_golden, load_pair
+from helpers import describe_misses, keypoint_parity, load_golden, load_pair, parity_entry
 
 pytestmark = pytest.mark.gpu
+
+# Descriptor bar of BASELINE.json: 1e-3 L2, asserted on the MAXIMUM over all compared rows.
+TOL = 1e-3
+# Rotated path: the orientation feeds sin/cos of every sample position, so a 1-ulp difference in `ori` moves samples
+# across cell / window boundaries. The reference's own orientation is not reproducible run to run (shared-memory float
+# atomics, surfd.cu:1795-1805): profiles/r2_ref_spread.json records its run-to-run spread on the same frames; the bar
+# here is max(1e-3, that spread) -- see ROT_TOL_NOTE in DESIGN.md section 5.
+TOL_ROT = 1e-3
 
 REF = pytest.mark.skipif(not ref_lib.available(), reason="oracle/_ref/libsurfref.so not built")
 
@@ -104,7 +112,7 @@ def test_integral_unaligned_pitch(pitch_pad):
 
 @pytest.mark.parametrize("w,h,seed,noct", CASES[:4])
 @pytest.mark.parametrize("upright", [True, False])
-def test_keypoints_and_descriptors_vs_oracle(w, h, seed, noct, upright):
+def test_keypoints_and_descriptors_vs_oracle(w, h, seed, noct, upright, report):
     sb = _sb()
     img = sb.synth_frame(w, h, seed)
     det = make_det(w, h, noct, upright=upright)
@@ -118,13 +126,18 @@ def test_keypoints_and_descriptors_vs_oracle(w, h, seed, noct, upright):
     # descriptors of matched keypoints (positions agree to float round-off, so descriptors do too)
     exact = ok & (np.abs(pts["x"][idx] - opts["x"]) < 1e-4) & (np.abs(pts["y"][idx] - opts["y"]) < 1e-4) & \
         (np.abs(pts["scale"][idx] - opts["scale"]) < 1e-5)
+    dori = None
     if not upright:
         dori = np.abs(np.angle(np.exp(1j * (pts["ori"][idx] - opts["ori"]))))
         assert np.median(dori[ok]) < 1e-4
-        exact &= dori < 1e-5
-    assert exact.sum() >= 0.9 * ok.sum()
+    # every matched keypoint is compared; the ones whose position differs by more than round-off are LISTED
+    l2_all = np.linalg.norm(desc[idx[ok]] - odesc[ok], axis=1)
+    report(**parity_entry(f"{w}x{h} seed {seed} upright={upright} vs oracle", opts, pts, ok, idx, miss_r, miss_g, l2_all,
+                          extra={"position_differs_over_1e-4": int((ok & ~exact).sum()),
+                                 "ori_diff_max": None if dori is None else float(dori[ok].max())}))
+    assert (ok & ~exact).sum() <= max(1, ok.sum() // 100), f"{(ok & ~exact).sum()} matched keypoints differ in position by > 1e-4"
     l2 = np.linalg.norm(desc[idx[exact]] - odesc[exact], axis=1)
-    assert l2.max() <= 1e-3, f"descriptor L2 max {l2.max():.3e}"
+    assert l2.max() <= (TOL if upright else TOL_ROT), f"descriptor L2 max {l2.max():.3e}"
 
 
 def test_describe_given_points_matches_oracle_exact_inputs():
@@ -154,21 +167,23 @@ def test_describe_given_points_matches_oracle_exact_inputs():
         bad = np.isnan(l2)
         assert not bad.any()
         # rotated descriptors inherit the orientation's round-off through sin/cos
-        assert l2.max() <= (1e-3 if upright else 5e-3), f"upright={upright} extend={extend}: L2 max {l2.max():.3e}"
+        assert l2.max() <= (TOL if upright else TOL_ROT), f"upright={upright} extend={extend}: L2 max {l2.max():.3e}"
 
 
 @REF
 @pytest.mark.parametrize("which", ["left", "right"])
-def test_bundled_pair_vs_reference(which):
-    """config 1 of BASELINE.md: main.cpp defaults on the reference's own stereo pair"""
+@pytest.mark.parametrize("upright", [True, False])
+def test_bundled_pair_vs_reference(which, upright, report):
+    """config 1 of BASELINE.md: main.cpp defaults on the reference's own stereo pair (and once with upright=false)"""
     left, right = load_pair()
     img = left if which == "left" else right
     h, w = img.shape
-    ref = ref_lib.Reference(w, h, 4, 4.0, False, 9, 2, True, False, 4)
+    ref = ref_lib.Reference(w, h, 4, 4.0, False, 9, 2, upright, False, 4)
+    ref.detect(img, max_pts=32768)  # the reference's first call reads uninitialised scratch (SURVEY.md 2.4-4)
     rpts, rdesc = ref.detect(img, max_pts=32768)
     rI, rlayers, _ = ref.stages(img)
     ref.close()
-    det = make_det(w, h, 4)
+    det = make_det(w, h, 4, upright=upright)
     data, pts, desc = run_detect(det, img)
     assert np.array_equal(det.get_integral(), rI)
     for o, (g, wnt) in enumerate(zip(det.split_response(det.get_response()), rlayers)):
@@ -177,7 +192,9 @@ def test_bundled_pair_vs_reference(which):
     assert fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\nreference-only:\n{describe_misses(miss_r, 4.0)}\nours-only:\n{describe_misses(miss_g, 4.0)}"
     assert np.array_equal(pts["laplace"][idx[ok]], rpts["laplace"][ok])
     l2 = np.linalg.norm(desc[idx[ok]] - rdesc[ok], axis=1)
-    assert (l2 <= 1e-3).mean() >= 0.99, f"descriptor L2: max {l2.max():.3e}, frac ok {(l2 <= 1e-3).mean():.4f}"
+    report(**parity_entry(f"bundled {which} upright={upright} vs reference", rpts, pts, ok, idx, miss_r, miss_g, l2))
+    assert len(rpts) == (2739 if which == "left" else 3443)
+    assert l2.max() <= (TOL if upright else TOL_ROT), f"descriptor L2: max {l2.max():.3e}, rows over: {(l2 > TOL).sum()}"
 
 
 @REF
@@ -202,7 +219,7 @@ def test_describe_vs_reference_same_points(upright, extend):
         assert np.nanmax(dori) < 1e-3, f"orientation differs by {np.nanmax(dori)}"
     l2 = np.linalg.norm(got - rdesc, axis=1)
     assert np.isfinite(l2).all()
-    assert l2.max() <= (1e-3 if upright else 5e-3), f"L2 max {l2.max():.3e}"
+    assert l2.max() <= (TOL if upright else TOL_ROT), f"L2 max {l2.max():.3e}"
 
 
 @REF
@@ -444,7 +461,7 @@ def test_doubled_vs_oracle(w, h, upright):
     fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(opts, pts)
     assert len(opts) > 100 and fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\n{describe_misses(miss_r, 4.0)}"
     l2 = np.linalg.norm(desc[idx[ok]] - odesc[ok], axis=1)
-    assert (l2 <= (1e-3 if upright else 5e-3)).mean() >= 0.99, f"descriptor L2 max {l2.max():.3e}"
+    assert l2.max() <= (TOL if upright else TOL_ROT), f"descriptor L2 max {l2.max():.3e}"
 
 
 @REF
@@ -464,7 +481,7 @@ def test_doubled_vs_reference():
     fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(rpts, pts)
     assert len(rpts) > 100 and fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\n{describe_misses(miss_r, 4.0)}"
     l2 = np.linalg.norm(desc[idx[ok]] - rdesc[ok], axis=1)
-    assert (l2 <= 1e-3).mean() >= 0.99, f"descriptor L2 max {l2.max():.3e}"
+    assert l2.max() <= TOL, f"descriptor L2 max {l2.max():.3e}"
 
 
 def test_match_filter_ratio_laplace_cross():
@@ -537,7 +554,7 @@ def test_init_argument_variants_vs_oracle(kw):
     assert fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\n{describe_misses(miss_r, a['thresh'])}"
     assert desc.shape[1] == odesc.shape[1] == a["desc_wsz"] ** 2 * (8 if a["extend"] else 4)
     l2 = np.linalg.norm(desc[idx[ok]] - odesc[ok], axis=1)
-    assert (l2 <= (1e-3 if a["upright"] else 5e-3)).mean() >= 0.99, f"descriptor L2 max {l2.max():.3e}"
+    assert l2.max() <= (TOL if a["upright"] else TOL_ROT), f"descriptor L2 max {l2.max():.3e}"
     # matching for this descriptor size (16/32/36-d take the generic kernel, 64/128-d the tensor-core one)
     torch = _torch()
     d_img, whp = upload(img)
@@ -553,3 +570,83 @@ def test_init_argument_variants_vs_oracle(kw):
         assert np.array_equal(got["match"], want["match"])
         assert np.allclose(got["score"], want["score"], rtol=0, atol=1e-6)
         assert np.allclose(got["ambiguity"], want["ambiguity"], rtol=0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------- full-size parity vs the reference
+
+@REF
+@pytest.mark.parametrize("w,h,seed", [(1920, 1080, 1), (3840, 2160, 2)])
+@pytest.mark.parametrize("upright", [True, False])
+def test_full_size_vs_reference(w, h, seed, upright, report):
+    """BASELINE configs[1] (1920x1080, seed 1) and configs[2] (3840x2160, seed 2): keypoints and descriptors against the
+    unmodified reference on the same frame, upright and rotated, every disagreement listed in the parity report."""
+    sb = _sb()
+    img = sb.synth_frame(w, h, seed)
+    ref = ref_lib.Reference(w, h, 5, 4.0, False, 9, 2, upright, False, 4)
+    ref.detect(img, max_pts=65536)  # discard the first call (SURVEY.md 2.4-4)
+    rpts, rdesc = ref.detect(img, max_pts=65536)
+    rI, rlayers, _ = ref.stages(img)
+    ref.close()
+    det = make_det(w, h, 5, upright=upright, max_pts=65536)
+    data, pts, desc = run_detect(det, img, max_pts=65536)
+    assert np.array_equal(det.get_integral(), rI)
+    for o, (g, wnt) in enumerate(zip(det.split_response(det.get_response()), rlayers)):
+        assert_resp_close(g, wnt, f"octave {o}")
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(rpts, pts)
+    l2 = np.linalg.norm(desc[idx[ok]] - rdesc[ok], axis=1)
+    dori = np.abs(np.angle(np.exp(1j * (pts["ori"][idx[ok]] - rpts["ori"][ok])))) if not upright else np.zeros(1)
+    report(**parity_entry(f"{w}x{h} seed {seed} upright={upright} vs reference", rpts, pts, ok, idx, miss_r, miss_g, l2,
+                          extra={"ori_diff_max": float(dori.max())}))
+    assert len(rpts) > 4000 and fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\nreference-only:\n{describe_misses(miss_r, 4.0)}\nours-only:\n{describe_misses(miss_g, 4.0)}"
+    assert np.array_equal(pts["laplace"][idx[ok]], rpts["laplace"][ok])
+    assert l2.max() <= (TOL if upright else TOL_ROT), f"descriptor L2 max {l2.max():.3e}, rows over: {(l2 > TOL).sum()} of {len(l2)}"
+
+
+@REF
+def test_stereo_1080p_match_vs_reference(report):
+    """BASELINE configs[4] at full size: two 1080p stereo pairs (left seed 5000+p, right = the same texture 12 px to the
+    side + noise), detect + describe here, matched here and by the reference's Surfor::match on the SAME descriptors:
+    indices, scores and ambiguities must be equal row by row."""
+    sb = _sb()
+    torch = _torch()
+    w, h = 1920, 1080
+    det = make_det(w, h, 5, max_pts=32768)
+    ref = ref_lib.Reference(w, h, 5)
+    for p in range(2):
+        sl = sb.synth_frame(w, h, 5000 + p)
+        sr = sb.synth_frame(w, h, 5000 + p, 12, 2, (5000 + p) ^ 0xA5A5)
+        d1, p1, f1 = run_detect(det, sl)
+        d2, p2, f2 = run_detect(det, sr)
+        det.match(d1, d2, torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda())
+        got = d1.host_points()
+        want = ref.match(p1, f1, p2, f2)
+        diff = np.nonzero(got["match"] != want["match"])[0]
+        report(case=f"stereo pair {p} 1080p", n1=int(len(p1)), n2=int(len(p2)), match_rows_differing=[int(i) for i in diff[:40]],
+               match_rows_differing_count=int(len(diff)), accepted_ambiguity_lt_0p8=int((got["ambiguity"] < 0.8).sum()),
+               score_max_abs_diff=float(np.abs(got["score"] - want["score"]).max()),
+               ambiguity_max_abs_diff=float(np.abs(got["ambiguity"] - want["ambiguity"]).max()))
+        assert len(p1) > 4000 and len(p2) > 4000
+        assert len(diff) == 0, f"pair {p}: match index differs in rows {diff[:10]}"
+        assert np.array_equal(got["score"], want["score"])
+        assert np.allclose(got["ambiguity"], want["ambiguity"], rtol=0, atol=1e-6)
+        assert np.array_equal(got["match_x"], want["match_x"]) and np.array_equal(got["match_y"], want["match_y"])
+    ref.close()
+
+
+def test_low_threshold_candidate_queue_cannot_overflow(report):
+    """thresh 0.05 at 1080p: an order of magnitude more candidates than at the default threshold. The candidate queue has
+    one slot per NMS cell (sb_info.cand_capacity), so nothing is dropped: the keypoint set equals the oracle's."""
+    sb = _sb()
+    w, h = 1920, 1080
+    img = sb.synth_frame(w, h, 1)
+    cap = 262144
+    det = sb.Surfor()
+    det.init(5, 0.05, False, 9, 2, True, False, 4, w, h, max_pts=cap)
+    assert det.info.cand_capacity >= 300000  # 0.32 M cells at 1080p (SURVEY.md 3.5)
+    data, pts, _ = run_detect(det, img, max_pts=cap, desc=False)
+    opts, _ = ol.Oracle(5, 0.05, False, 9, 2, True, False, 4).detect_and_compute(img, max_pts=cap, desc=False)
+    fr, fg, ok, idx, miss_r, miss_g = keypoint_parity(opts, pts)
+    report(**parity_entry("1080p seed 1 thresh 0.05 vs oracle", opts, pts, ok, idx, miss_r, miss_g, thresh=0.05))
+    assert len(opts) > 20000 and len(pts) < cap, (len(opts), len(pts))
+    assert abs(len(pts) - len(opts)) <= len(opts) // 200, (len(pts), len(opts))
+    assert fr >= 0.99 and fg >= 0.99, f"{fr:.4f}/{fg:.4f}\n{describe_misses(miss_r, 0.05)}"
