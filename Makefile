@@ -4,7 +4,7 @@ PKG    := cuda-surf_b200
 CSRC   := $(PKG)/csrc
 LIB    := $(PKG)/libsurfb200.so
 NVFLAGS := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Iinclude -I$(CSRC)
-CU_SRCS := $(CSRC)/integral.cu $(CSRC)/hessian.cu $(CSRC)/nms.cu $(CSRC)/describe.cu $(CSRC)/match.cu $(CSRC)/postmatch.cu
+CU_SRCS := $(CSRC)/integral.cu $(CSRC)/hessian.cu $(CSRC)/nms.cu $(CSRC)/describe.cu $(CSRC)/describe_tma.cu $(CSRC)/match.cu $(CSRC)/postmatch.cu
 OBJS    := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS)) build/ctx.o build/synth.o
 
 all: $(LIB) demo

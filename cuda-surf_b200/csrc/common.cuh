@@ -117,15 +117,34 @@ cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, c
                            cudaStream_t st);
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
                        int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st);
+// What the TMA descriptor path (describe_tma.cu) needs besides the integral image: the tensor maps over the context's
+// integral buffer, the per-slot keypoint class lists [batch][2][max_pts] and their counters [batch][4] = {keypoints on the
+// TMA path, on the gather path, work counter of either kernel}, zero on entry (clamp_counts_kernel / sb_describe re-arm them).
+struct DescAux {
+    const void* maps = nullptr;   // device array of CUtensorMap (128 B each); nullptr: gather kernel only
+    int* cls_idx = nullptr;
+    int* cls_cnt = nullptr;
+    int slot0 = 0;                // first frame slot of this launch inside the context's buffers
+};
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
-                            int* d_work, int* d_work_orient /* one zeroed int per frame each */, cudaStream_t st);
-cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, int* d_work_orient,
+                            int* d_work, int* d_work_orient /* one zeroed int per frame each */, const DescAux& aux, cudaStream_t st);
+cudaError_t build_describe_maps(const PipeP& P, const int* d_integral, int batch, void** d_maps);
+bool describe_tma_applies(const PipeP& P);
+cudaError_t launch_describe_tma(const PipeP& P, int nframes, const DescAux& aux, sb_point* d_points, long long pts_stride,
+                                const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
                                 cudaStream_t st);
+cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, int* d_work_orient,
+                                int* d_cls_cnt /* 4 ints per frame, may be null */, cudaStream_t st);
 // grow-only device scratch of the matcher (split-bf16 operands, per-split group top-2), owned by the context
 struct MatchScratch {
     void* a = nullptr; void* b = nullptr; void* part = nullptr;
     size_t cap_a = 0, cap_b = 0, cap_part = 0;
+    // the two tensor maps of the last call (CUtensorMap is 128 bytes) and what they were encoded for: a caller that matches
+    // sets of the same padded sizes again -- a video stream -- does not pay cuTensorMapEncodeTiled twice per call
+    alignas(64) unsigned char map_a[128], map_b[128];
+    const void* map_a_base = nullptr; const void* map_b_base = nullptr;
+    int map_a_rows = 0, map_b_rows = 0, map_nf = 0;
 };
 cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
                          int nfeatures, MatchScratch& ws, int sm_count, cudaStream_t st);

@@ -60,6 +60,10 @@ struct sb_ctx {
     int* d_cand_count = nullptr;
     int* d_work = nullptr;        // per-slot work counter of the descriptor kernel (zeroed by clamp_counts)
     int cand_cap = 0;
+    // TMA descriptor path (describe_tma.cu): tensor maps over d_integral, keypoint class lists and their counters
+    void* d_desc_maps = nullptr;
+    int* d_cls_idx = nullptr;
+    int* d_cls_cnt = nullptr;
     uint8_t* d_up = nullptr;  // doubled=true: the 2x up-sampled frames, `batch` slots of up_pitch * P.h bytes
     int up_pitch = 0;
     int* h_counts = nullptr;          // pinned
@@ -202,6 +206,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_integral); cudaFree(ctx->d_integral_ph); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
     cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_work); cudaFree(ctx->d_desc_own);
+    cudaFree(ctx->d_desc_maps); cudaFree(ctx->d_cls_idx); cudaFree(ctx->d_cls_cnt);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     free_match_scratch(ctx->match_ws);
     if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
@@ -270,6 +275,15 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     ok(cudaMalloc((void**)&c->d_cand, sizeof(unsigned) * (size_t)c->cand_cap * B));
     ok(cudaMalloc((void**)&c->d_cand_count, sizeof(int) * B));
     ok(cudaMalloc((void**)&c->d_work, sizeof(int) * 2 * B));  // [0, B): descriptor pass, [B, 2B): orientation pass
+    // opt-in (environment, read at context creation): the TMA-staged descriptor kernel for step-2 keypoints. Measured
+    // on the B200 it is as fast as the gather kernel on those keypoints, not faster, so the default stays off.
+    const char* tma_env = getenv("SURFB200_DESCRIBE_TMA");
+    if (tma_env && atoi(tma_env) != 0 && describe_tma_applies(P)) {
+        ok(cudaMalloc((void**)&c->d_cls_idx, sizeof(int) * 2 * (size_t)P.max_pts * B));
+        ok(cudaMalloc((void**)&c->d_cls_cnt, sizeof(int) * 4 * B));
+        if (e == cudaSuccess) ok(cudaMemset(c->d_cls_cnt, 0, sizeof(int) * 4 * B));
+        if (e == cudaSuccess) ok(build_describe_maps(P, c->d_integral, B, &c->d_desc_maps));
+    }
     if (P.doubled) {
         c->up_pitch = align_up(P.w, 128);
         ok(cudaMalloc((void**)&c->d_up, (size_t)c->up_pitch * P.h * B));
@@ -312,7 +326,8 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
     const bool fast0 = P.sampling == 2 && P.init_lobe == 3 && P.max_scale == 5;
     const int nhess = fast0 ? (P.noctaves > 1 ? 2 : 1) : 1;
     info->cand_capacity = ctx->cand_cap;
-    info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + nhess + 2 /*nms scan, refine*/ + 1 /*clamp*/ + (P.upright ? 1 : 2);
+    info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + nhess + 2 /*nms scan, refine*/ + 1 /*clamp*/ + (P.upright ? 1 : 2) +
+                              (ctx->d_desc_maps ? 2 : 0) /*classify + TMA descriptor kernel*/;
     return SB_OK;
 }
 
@@ -345,11 +360,14 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
     CU(launch_nms(P, nframes, integral, resp, d_points, d_counts, ctx->d_cand + (size_t)slot0 * ctx->cand_cap,
                   ctx->d_cand_count + slot0, ctx->cand_cap, st));
     CU(launch_clamp_counts(d_counts, nframes, P.max_pts, ctx->d_cand_count + slot0, ctx->d_work + slot0,
-                           ctx->d_work + ctx->prm.batch + slot0, st));
+                           ctx->d_work + ctx->prm.batch + slot0, ctx->d_cls_cnt ? ctx->d_cls_cnt + 4 * slot0 : nullptr, st));
     if (ev) CU(cudaEventRecord(ev[3], st));
-    if (d_desc)
+    if (d_desc) {
+        DescAux aux;
+        aux.maps = ctx->d_desc_maps; aux.cls_idx = ctx->d_cls_idx; aux.cls_cnt = ctx->d_cls_cnt; aux.slot0 = slot0;
         CU(launch_describe(P, nframes, integral, d_points, P.max_pts, d_counts, -1, d_desc,
-                           (long long)P.max_pts * P.nfeatures, ctx->sm_count, ctx->d_work + slot0, ctx->d_work + ctx->prm.batch + slot0, st));
+                           (long long)P.max_pts * P.nfeatures, ctx->sm_count, ctx->d_work + slot0, ctx->d_work + ctx->prm.batch + slot0, aux, st));
+    }
     if (ev) CU(cudaEventRecord(ev[4], st));
     return SB_OK;
 }
@@ -768,8 +786,12 @@ extern "C" int sb_describe(sb_ctx* ctx, int slot, sb_point* d_points, int n, flo
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->d_work + slot, 0, sizeof(int), ctx->stream));
     CU(cudaMemsetAsync(ctx->d_work + ctx->prm.batch + slot, 0, sizeof(int), ctx->stream));
+    DescAux aux;
+    // (the class lists hold max_pts indices per slot: a longer caller-supplied list takes the gather kernel only)
+    if (n <= P.max_pts) { aux.maps = ctx->d_desc_maps; aux.cls_idx = ctx->d_cls_idx; aux.cls_cnt = ctx->d_cls_cnt; aux.slot0 = slot; }
+    if (aux.maps) CU(cudaMemsetAsync(ctx->d_cls_cnt + 4 * slot, 0, 4 * sizeof(int), ctx->stream));
     CU(launch_describe(P, 1, ctx->d_integral + (size_t)slot * P.istride, d_points, 0, nullptr, n, d_desc, 0, ctx->sm_count, ctx->d_work + slot,
-                       ctx->d_work + ctx->prm.batch + slot, ctx->stream));
+                       ctx->d_work + ctx->prm.batch + slot, aux, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SB_OK;
 }

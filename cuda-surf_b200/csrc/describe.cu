@@ -465,7 +465,8 @@ template <int O>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
 describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
-                        long long desc_stride, int* __restrict__ work) {
+                        long long desc_stride, int* __restrict__ work, const int* __restrict__ cls_idx, int* __restrict__ cls_cnt,
+                        int slot0) {
     extern __shared__ __align__(16) float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -480,7 +481,10 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     float* T = smem + warp * stage;
     float* Wc = T + W * O * kTS;
     const unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut2);
-    const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
+    // with a class list (describe_tma.cu) this kernel takes the keypoints the TMA path left: list position -> keypoint
+    const int* list = cls_idx ? cls_idx + ((size_t)(slot0 + f) * 2 + 1) * P.max_pts : nullptr;
+    int* wk = cls_cnt ? cls_cnt + (slot0 + f) * 4 + 3 : work + f;  // this frame's work counter
+    const int n = list ? cls_cnt[(slot0 + f) * 4 + 1] : (fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts));
     const int ip = P.ip;
     const int* I = Ibase + (size_t)f * P.istride + ip;
     const sb_point* pts = points + (size_t)f * pts_stride;
@@ -490,7 +494,8 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
 
     // a warp's first keypoint is fixed, the following ones come from a per-frame counter (zero on entry): keypoints cost
     // 2 or 3 passes, and with one or two per warp (single frame) a static split left the machine waiting for the unlucky warps
-    for (int pi = blockIdx.x * kWarpsPerCta + warp; pi < n;) {
+    for (int pk = blockIdx.x * kWarpsPerCta + warp; pk < n;) {
+        const int pi = list ? list[pk] : pk;
         const float x = pts[pi].x, y = pts[pi].y;
         const KpGeom kg = kp_geom(x, y, pts[pi].scale, W, P.mag_factor, P.doubled);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};  // descriptor elements lane, lane+32, ... (un-normalised)
@@ -712,16 +717,24 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
         }
         __syncwarp();
         int nxt = 0;
-        if (lane == 0) nxt = gridDim.x * kWarpsPerCta + atomicAdd(work + f, 1);
-        pi = __shfl_sync(0xffffffffu, nxt, 0);
+        if (lane == 0) nxt = gridDim.x * kWarpsPerCta + atomicAdd(wk, 1);
+        pk = __shfl_sync(0xffffffffu, nxt, 0);
     }
 }
 
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
-                            int* d_work, int* d_work_orient, cudaStream_t st) {
+                            int* d_work, int* d_work_orient, const DescAux& aux, cudaStream_t st) {
     const int maxn = fixed_count >= 0 ? fixed_count : P.max_pts;
     if (maxn <= 0 || nframes <= 0) return cudaSuccess;
+    // upright 64-d: the keypoints with sampling step 2 go through the TMA-staged kernel, the gather kernel below takes the rest
+    const bool tma = aux.maps && describe_tma_applies(P);
+    if (tma) {
+        const cudaError_t e = launch_describe_tma(P, nframes, aux, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, sm_count, st);
+        if (e != cudaSuccess) return e;
+    }
+    const int* cls_idx = tma ? aux.cls_idx : nullptr;
+    int* cls_cnt = tma ? aux.cls_cnt : nullptr;
     const int need = (maxn + kWarpsPerCta - 1) / kWarpsPerCta;
     // blockIdx.x runs fastest, so 1-2 CTAs per SM per frame keep only a few frames' integral images
     // live at a time (L2-resident; measured: 1 is best from 32 frames, 2 at 8) while still covering the machine for a single frame
@@ -736,10 +749,10 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
         const size_t smem = ((size_t)kWarpsPerCta * (P.desc_wsz * P.orient_size + P.desc_wsz) * kTS + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
         if (P.orient_size == 4) {
             cudaFuncSetAttribute(describe_upright_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            describe_upright_kernel<4><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work);
+            describe_upright_kernel<4><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, cls_idx, cls_cnt, aux.slot0);
         } else {
             cudaFuncSetAttribute(describe_upright_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            describe_upright_kernel<8><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work);
+            describe_upright_kernel<8><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, nullptr, nullptr, 0);
         }
     } else {
         const size_t smem = ((size_t)kWarpsPerCta * (2 * kRotRows + 32) + (size_t)kWarpsPerCta * (P.nfeatures + 8) * 32 + 40) * sizeof(float);

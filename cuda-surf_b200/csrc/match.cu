@@ -25,6 +25,7 @@
 //                   So score / match are those of the reference unless two candidates of one group
 //                   are closer than the split-bf16 error to the group's second place.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -45,7 +46,8 @@ template <int NF> struct MatchCfg {
     static constexpr int BN = NF == 64 ? 128 : 64;     // columns (descriptors of set 2) per tile: two stages must fit
     static constexpr int A_BYTES = KCH * kBM * kSwizzleRow;
     static constexpr int B_BYTES = KCH * BN * kSwizzleRow;
-    static constexpr int SMEM = A_BYTES + kStages * B_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+    static constexpr int XCHG_BYTES = kBM * 8 * 16;  // top-2 of the upper column half, handed to the lower half's warps
+    static constexpr int SMEM = A_BYTES + kStages * B_BYTES + XCHG_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
     static constexpr int TMEM_COLS = kStages * BN;     // 256 / 128: a power of two >= 32
 };
 
@@ -124,24 +126,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <int NF>
 __global__ void match_prep(const float* __restrict__ fa, int na, int na_pad, __nv_bfloat16* __restrict__ outa,
                            const float* __restrict__ fb, int nb, int nb_pad, __nv_bfloat16* __restrict__ outb) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // match_mma's prologue overlaps this kernel
+    // a thread converts 8 consecutive elements of a row: two 128-bit loads, three 128-bit stores (hi, and lo / hi again)
+    constexpr int PER = NF / 8;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = t / NF;
-    const int d = t - row * NF;
+    int row = t / PER;
+    const int d = (t - row * PER) * 8;
     const bool is_b = row >= na_pad;
     if (is_b) row -= na_pad;
     if (is_b && row >= nb_pad) return;
     const float* f = is_b ? fb : fa;
     const int nvalid = is_b ? nb : na;
-    __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (row < nvalid) {
-        const float v = __ldg(f + (size_t)row * NF + d);
-        hi = __float2bfloat16_rn(v);
-        lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const float4 x = __ldg(reinterpret_cast<const float4*>(f + (size_t)row * NF + d));
+        const float4 y = __ldg(reinterpret_cast<const float4*>(f + (size_t)row * NF + d) + 1);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    }
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        hi[k] = __float2bfloat16_rn(v[k]);
+        lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
     }
     __nv_bfloat16* o = (is_b ? outb : outa) + (size_t)row * (3 * NF) + d;
-    o[0] = hi;
-    o[NF] = is_b ? lo : hi;
-    o[2 * NF] = is_b ? hi : lo;
+    const uint4 h4 = *reinterpret_cast<const uint4*>(hi), l4 = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(o) = h4;
+    *reinterpret_cast<uint4*>(o + NF) = is_b ? l4 : h4;
+    *reinterpret_cast<uint4*>(o + 2 * NF) = is_b ? h4 : l4;
 }
 
 // ---------------------------------------------------------------------------- 2. tensor-core scores + fused group top-2
@@ -152,7 +164,7 @@ struct __align__(16) Top2 { float mx, sc; int imx, isc; };  // 16 bytes, moved a
 // epilogue of tile i-1 out of TMEM. Per stage three mbarriers: `full` (TMA landed), `mma` (tcgen05.commit: accumulator
 // ready, operands consumed), `free` (the eight epilogue warps have read the accumulator). Round-1 v1 did load -> MMA ->
 // epilogue strictly one after the other (ncu: tensor pipe active 12.5 % of the kernel).
-template <int NF>
+template <int NF, bool KEYS>
 __global__ void __launch_bounds__((kEpiWarps + 1) * 32, 1)
 match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles, int tiles_per_split,
           int n1pad, Top2* __restrict__ part) {
@@ -162,8 +174,10 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                    // KCH chunks of 128 rows x 128 B
     uint8_t* sB = smem + Cfg::A_BYTES;     // kStages x (KCH chunks of BN rows x 128 B)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + kStages * Cfg::B_BYTES);
+    float4* xchg = reinterpret_cast<float4*>(smem + Cfg::A_BYTES + kStages * Cfg::B_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + kStages * Cfg::B_BYTES + Cfg::XCHG_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // match_final's CTAs may take their places now
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rb = blockIdx.x, split = blockIdx.y;
     const int t0 = split * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
@@ -172,10 +186,24 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     auto bar_mma = [&](int st) { return smem_u32(&bars[kStages + st]); };
     auto bar_free = [&](int st) { return smem_u32(&bars[2 * kStages + st]); };
 
-    if (tid == 0) {
+    constexpr uint32_t idesc = umma_idesc(kBM, BN);
+    auto issue_tma = [&](int i) {  // tile t0+i into stage i % kStages (and, once, the CTA's rows of A')
+        const int st = i % kStages;
+        mbar_expect_tx(bar_full(st), Cfg::B_BYTES + (i == 0 ? Cfg::A_BYTES : 0));
+        if (i == 0)
+            for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sA + c * kBM * kSwizzleRow), &mapA, bar_full(st), c * 64, rb * kBM);
+        for (int c = 0; c < KCH; c++)
+            tma_load_2d(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow), &mapB, bar_full(st), c * 64, (t0 + i) * BN);
+    };
+    if (tid == kEpiWarps * 32) {
+        // the producer thread arms the barriers itself and starts the first loads at once: they fly while warp 1 allocates
+        // tensor memory and the CTA meets at the barrier below
         for (int st = 0; st < kStages; st++) { mbar_init(bar_full(st), 1); mbar_init(bar_mma(st), 1); mbar_init(bar_free(st), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // (programmatic dependent launch: everything above overlaps match_prep; its output is first touched here)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (n > 0) issue_tma(0);
     }
     if (warp == 1) {  // TMEM: kStages accumulators of BN fp32 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
@@ -189,16 +217,6 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     if (warp == kEpiWarps) {
         // ------------------------------------------------------------------ producer: one thread
         if (lane == 0 && n > 0) {
-            constexpr uint32_t idesc = umma_idesc(kBM, BN);
-            auto issue_tma = [&](int i) {  // tile t0+i into stage i % kStages (and, once, the CTA's rows of A')
-                const int st = i % kStages;
-                mbar_expect_tx(bar_full(st), Cfg::B_BYTES + (i == 0 ? Cfg::A_BYTES : 0));
-                if (i == 0)
-                    for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sA + c * kBM * kSwizzleRow), &mapA, bar_full(st), c * 64, rb * kBM);
-                for (int c = 0; c < KCH; c++)
-                    tma_load_2d(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow), &mapB, bar_full(st), c * 64, (t0 + i) * BN);
-            };
-            issue_tma(0);
             for (int i = 0; i < n; i++) {
                 const int st = i % kStages, use = i / kStages;
                 if (i + 1 < n) {
@@ -228,13 +246,45 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         int imx[8], isc[8];
 #pragma unroll
         for (int g = 0; g < 8; g++) { mx[g] = 0.f; sc[g] = 0.f; imx[g] = -1; isc[g] = -1; }
+        // Inside a round of up to kRound tiles the running top-2 of a group is kept on PACKED KEYS: the score's bit pattern
+        // with its low 6 mantissa bits replaced by 63 - (candidate number inside the round). Positive floats order like
+        // signed integers, so a score costs one LOP3 and three integer min/max instead of two compares, three selects
+        // and three float min/max (ncu of round 1: the epilogue's 9 instructions per score, not the tensor pipe, set the
+        // kernel's time). The key drops 2^-17 of the score -- below the 2e-5 of the split-bf16 product, and like it only
+        // a matter of WHICH two candidates match_final re-scores exactly; equal truncated scores prefer the lower index,
+        // as the reference's strict > does. Key 0 = (score 0, candidate 63) is the empty slot.
+        constexpr int kRound = 63 / (BN / 16);  // BN/16 candidates of one group per tile and thread (BN/2 columns / 8 groups); code 63 = empty
+        int k1[8], k2[8];
+        auto fold = [&](int round0) {  // keys of the round starting at tile round0 -> (value, index), merged into the running top-2
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int key = q == 0 ? k1[g] : k2[g];
+                    const int code = 63 - (key & 63);
+                    if (code != 63) {
+                        // code = tile-in-round * (BN/16) + chunk * 4 + column-in-group
+                        const int per_tile = BN / 16;
+                        const int ti = code / per_tile, rest = code - ti * per_tile;
+                        const int col = (t0 + round0 + ti) * BN + chalf * (BN / 2) + (rest >> 2) * 32 + g * 4 + (rest & 3);
+                        const float s = __int_as_float(key & ~63);
+                        if (s > mx[g]) { sc[g] = mx[g]; isc[g] = imx[g]; mx[g] = s; imx[g] = col; }
+                        else if (s > sc[g]) { sc[g] = s; isc[g] = col; }
+                    }
+                }
+                k1[g] = 0; k2[g] = 0;
+            }
+        };
+#pragma unroll
+        for (int g = 0; g < 8; g++) { k1[g] = 0; k2[g] = 0; }
+        int round0 = 0;
         for (int i = 0; i < n; i++) {
             const int st = i % kStages, use = i / kStages;
+            if (KEYS && i - round0 == kRound) { fold(round0); round0 = i; }
             mbar_wait(bar_mma(st), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // thread == (row = TMEM lane, half of the columns); 32 accumulator columns per tcgen05.ld. Branch-free
-            // running top-2 per group: values with max/min, indices with selects; the 8 groups of a 32-column chunk
-            // are independent dependency chains (ILP 8).
+            // thread == (row = TMEM lane, half of the columns); 32 accumulator columns per tcgen05.ld; the 8 groups of a
+            // 32-column chunk are independent dependency chains (ILP 8).
 #pragma unroll 1
             for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
                 uint32_t r[32];
@@ -245,23 +295,58 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free(st)) : "memory");
                 }
-                const int col0 = (t0 + i) * BN + cb;  // multiple of 32: group of column j is (j % 32) / 4
+                // 63 - candidate number of column-in-group 0 of this chunk; the three others follow downwards
+                const int code0 = 63 - ((i - round0) * (BN / 16) + ((cb - chalf * (BN / 2)) >> 5) * 4);
+                if (KEYS) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int g = j >> 2;
-                    const float s = __uint_as_float(r[j]);
-                    const bool gt1 = s > mx[g], gt2 = s > sc[g];
-                    isc[g] = gt1 ? imx[g] : (gt2 ? col0 + j : isc[g]);
-                    imx[g] = gt1 ? col0 + j : imx[g];
-                    sc[g] = fmaxf(sc[g], fminf(mx[g], s));
-                    mx[g] = fmaxf(mx[g], s);
+                    for (int j = 0; j < 32; j++) {
+                        const int g = j >> 2;
+                        const int key = (int)(r[j] & 0xFFFFFFC0u) | (code0 - (j & 3));
+                        const int t = min(k1[g], key);
+                        k1[g] = max(k1[g], key);
+                        k2[g] = max(k2[g], t);
+                    }
+                } else {
+                    const int col0 = (t0 + i) * BN + cb;  // multiple of 32: group of column j is (j % 32) / 4
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const int g = j >> 2;
+                        const float s = __uint_as_float(r[j]);
+                        const bool gt1 = s > mx[g], gt2 = s > sc[g];
+                        isc[g] = gt1 ? imx[g] : (gt2 ? col0 + j : isc[g]);
+                        imx[g] = gt1 ? col0 + j : imx[g];
+                        sc[g] = fmaxf(sc[g], fminf(mx[g], s));
+                        mx[g] = fmaxf(mx[g], s);
+                    }
                 }
             }
         }
-        Top2* dst = part + ((size_t)(split * 2 + chalf) * n1pad + (size_t)rb * kBM + quarter * 32 + lane) * 8;
+        if (KEYS) fold(round0);
+        // The two column halves of a row meet here: the warps of the upper half pass their top-2 through shared memory
+        // (a named barrier over the 8 epilogue warps), the lower half's warps merge -- strict >, so equal scores keep
+        // the lower index, which is theirs -- and write ONE entry per (split, row, group).
+        const int row = quarter * 32 + lane;
+        if (chalf == 1) {
 #pragma unroll
-        for (int g = 0; g < 8; g++)
-            reinterpret_cast<float4*>(dst)[g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
+            for (int g = 0; g < 8; g++) xchg[row * 8 + g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (chalf == 0) {
+            Top2* dst = part + ((size_t)split * n1pad + (size_t)rb * kBM + row) * 8;
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const float4 o = xchg[row * 8 + g];
+                const float ov[2] = {o.x, o.y};
+                const int oi[2] = {__float_as_int(o.z), __float_as_int(o.w)};
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    if (oi[q] < 0) continue;
+                    if (ov[q] > mx[g]) { sc[g] = mx[g]; isc[g] = imx[g]; mx[g] = ov[q]; imx[g] = oi[q]; }
+                    else if (ov[q] > sc[g]) { sc[g] = ov[q]; isc[g] = oi[q]; }
+                }
+                reinterpret_cast<float4*>(dst)[g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -292,31 +377,32 @@ match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, c
             const float* __restrict__ f2, const Top2* __restrict__ part, int nsplit, int n1pad) {
     const int lane = threadIdx.x & 31;
     const int p1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // launched early (programmatic dependent launch): match_mma's partials
     if (p1 >= n1) return;
     const int g = (lane >> 1) & 7, k = lane & 1;
-    // tensor-core top-2 of the group across the splits (ties: lower index, as a running scan would keep)
+    // tensor-core top-2 of the group across the splits. The splits cover increasing column ranges and are taken in
+    // order, so strict > keeps the lower index on equal scores, as a running scan would.
     float v1 = 0.f, v2 = 0.f;
     int i1 = -1, i2 = -1;
     // (loads of eight splits are issued together: one L2 round trip per eight, not per split)
     for (int s0 = 0; s0 < nsplit; s0 += 8) {
-        Top2 cs[8];
+        float4 cs[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++)
-            if (s0 + u < nsplit) {  // 128 contiguous bytes per (split,row) across the warp, one 128-bit load per lane
-                const float4 w = __ldg(reinterpret_cast<const float4*>(part + ((size_t)(s0 + u) * n1pad + p1) * 8 + g));
-                cs[u] = Top2{w.x, w.y, __float_as_int(w.z), __float_as_int(w.w)};
-            } else {
-                cs[u] = Top2{0.f, 0.f, -1, -1};
-            }
+        for (int u = 0; u < 8; u++)  // 128 contiguous bytes per (split,row) across the warp, one 128-bit load per lane
+            cs[u] = s0 + u < nsplit ? __ldg(reinterpret_cast<const float4*>(part + ((size_t)(s0 + u) * n1pad + p1) * 8 + g))
+                                    : make_float4(0.f, 0.f, __int_as_float(-1), __int_as_float(-1));
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            const float cv[2] = {cs[u].mx, cs[u].sc};
-            const int ci[2] = {cs[u].imx, cs[u].isc};
+            const float cv[2] = {cs[u].x, cs[u].y};
+            const int ci[2] = {__float_as_int(cs[u].z), __float_as_int(cs[u].w)};
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-                if (ci[q] < 0) continue;
-                if (cv[q] > v1 || (cv[q] == v1 && i1 >= 0 && ci[q] < i1)) { v2 = v1; i2 = i1; v1 = cv[q]; i1 = ci[q]; }
-                else if (cv[q] > v2 || (cv[q] == v2 && i2 >= 0 && ci[q] < i2)) { v2 = cv[q]; i2 = ci[q]; }
+                const bool ok = ci[q] >= 0;
+                const bool gt1 = ok && cv[q] > v1, gt2 = ok && cv[q] > v2;
+                i2 = gt1 ? i1 : (gt2 ? ci[q] : i2);
+                v2 = gt1 ? v1 : (gt2 ? cv[q] : v2);
+                i1 = gt1 ? ci[q] : i1;
+                v1 = gt1 ? cv[q] : v1;
             }
         }
     }
@@ -458,7 +544,7 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     if (ntiles > 0) nsplit = (ntiles + tiles_per_split - 1) / tiles_per_split;
     // scratch (grow-only)
     const size_t needA = (size_t)n1pad * Cfg::KTOT * 2, needB = (size_t)n2pad * Cfg::KTOT * 2;
-    const size_t needP = (size_t)nsplit * 2 * n1pad * 8 * sizeof(Top2);  // two column halves per split
+    const size_t needP = (size_t)nsplit * n1pad * 8 * sizeof(Top2);
     cudaError_t e;
     auto grow = [&](void*& p, size_t& cap, size_t need) -> cudaError_t {
         if (cap >= need) return cudaSuccess;
@@ -471,13 +557,38 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     if ((e = grow(ws.b, ws.cap_b, needB)) != cudaSuccess) return e;
     if ((e = grow(ws.part, ws.cap_part, needP)) != cudaSuccess) return e;
 
-    match_prep<NF><<<((n1pad + n2pad) * NF + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a, d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b);
-    CUtensorMap mapA, mapB;
-    if (!make_map(&mapA, ws.a, n1pad, Cfg::KTOT, kBM) || !make_map(&mapB, ws.b, n2pad, Cfg::KTOT, Cfg::BN)) return cudaErrorNotSupported;
+    match_prep<NF><<<((n1pad + n2pad) * (NF / 8) + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a, d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b);
+    static_assert(sizeof(CUtensorMap) == sizeof(ws.map_a), "tensor map size");
+    CUtensorMap& mapA = *reinterpret_cast<CUtensorMap*>(ws.map_a);
+    CUtensorMap& mapB = *reinterpret_cast<CUtensorMap*>(ws.map_b);
+    if (ws.map_nf != NF || ws.map_a_base != ws.a || ws.map_a_rows != n1pad) {
+        if (!make_map(&mapA, ws.a, n1pad, Cfg::KTOT, kBM)) return cudaErrorNotSupported;
+        ws.map_a_base = ws.a; ws.map_a_rows = n1pad;
+    }
+    if (ws.map_nf != NF || ws.map_b_base != ws.b || ws.map_b_rows != n2pad) {
+        if (!make_map(&mapB, ws.b, n2pad, Cfg::KTOT, Cfg::BN)) return cudaErrorNotSupported;
+        ws.map_b_base = ws.b; ws.map_b_rows = n2pad;
+    }
+    ws.map_nf = NF;
     // per device (a process may hold contexts on several GPUs), so set on every launch
-    if ((e = cudaFuncSetAttribute(match_mma<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
-    match_mma<NF><<<dim3(rbs, nsplit), (kEpiWarps + 1) * 32, Cfg::SMEM, st>>>(mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
-    match_final<NF><<<(n1 + 3) / 4, 128, 0, st>>>(d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit * 2, n1pad);
+    static const bool use_pdl = !getenv("SB_MATCH_PDL") || atoi(getenv("SB_MATCH_PDL")) != 0;
+    static const bool use_keys = !getenv("SB_MATCH_KEYS") || atoi(getenv("SB_MATCH_KEYS")) != 0;
+    if ((e = cudaFuncSetAttribute(match_mma<NF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(match_mma<NF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
+    // match_mma and match_final are programmatic dependents of their predecessor: their CTAs are placed and run their
+    // prologue (barrier set-up, tensor-memory allocation) while it is still running, and wait at griddepcontrol.wait
+    // before they touch its output -- the three launches cost one ramp-up instead of three.
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(rbs, nsplit); cfg.blockDim = dim3((kEpiWarps + 1) * 32); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+    cfg.attrs = pdl; cfg.numAttrs = use_pdl ? 1 : 0;
+    if (use_keys) e = cudaLaunchKernelEx(&cfg, match_mma<NF, true>, mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
+    else e = cudaLaunchKernelEx(&cfg, match_mma<NF, false>, mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
+    if (e != cudaSuccess) return e;
+    cfg.gridDim = dim3((n1 + 3) / 4); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0;
+    if ((e = cudaLaunchKernelEx(&cfg, match_final<NF>, d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit, n1pad)) != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

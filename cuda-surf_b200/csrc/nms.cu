@@ -415,9 +415,12 @@ nms_refine_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
 
 // Clamp the keypoint counts to the capacity and re-arm the candidate counters for the next call (they are zero after
 // sb_create, and every pass leaves them zero again: no memset in the per-frame sequence).
-__global__ void clamp_counts_kernel(int* counts, int n, int max_pts, int* cand_count, int* work, int* work2) {
+__global__ void clamp_counts_kernel(int* counts, int n, int max_pts, int* cand_count, int* work, int* work2, int* cls_cnt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { counts[i] = min(counts[i], max_pts); cand_count[i] = 0; work[i] = 0; work2[i] = 0; }
+    if (i < n) {
+        counts[i] = min(counts[i], max_pts); cand_count[i] = 0; work[i] = 0; work2[i] = 0;
+        if (cls_cnt) *reinterpret_cast<int4*>(cls_cnt + 4 * i) = make_int4(0, 0, 0, 0);
+    }
 }
 
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
@@ -440,8 +443,8 @@ cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const
 }
 
 cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, int* d_work_orient,
-                                cudaStream_t st) {
-    clamp_counts_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(d_counts, nframes, max_pts, d_cand_count, d_work, d_work_orient);
+                                int* d_cls_cnt, cudaStream_t st) {
+    clamp_counts_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(d_counts, nframes, max_pts, d_cand_count, d_work, d_work_orient, d_cls_cnt);
     return cudaGetLastError();
 }
 
