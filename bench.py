@@ -235,14 +235,14 @@ def run_ours(args, rank, world, local_rank, dist):
     out = [(h_pts, h_cnt, h_desc),
            (torch.zeros_like(h_pts).pin_memory(), torch.zeros_like(h_cnt).pin_memory(), torch.zeros_like(h_desc).pin_memory())]
 
-    def e2e_steps(k):
+    def e2e_steps(k, with_desc=True):
         tickets = []
         for i in range(k):
             tickets.append(det.submit_batch_host(h_frames))
             if i >= 2:  # two batches submitted ahead: k downloads, k+1 computes, k+2 uploads
-                det.wait_batch_host(tickets[i - 2], *out[i & 1])
+                det.wait_batch_host(tickets[i - 2], *(out[i & 1] if with_desc else out[i & 1][:2]))
         for i in range(max(0, k - 2), k):
-            det.wait_batch_host(tickets[i], *out[i & 1])
+            det.wait_batch_host(tickets[i], *(out[i & 1] if with_desc else out[i & 1][:2]))
 
     e2e_steps(max(3, args.warmup // 2))
     barrier()
@@ -265,6 +265,22 @@ def run_ours(args, rank, world, local_rank, dist):
     ts = torch.tensor([(t3 - t2) / ns], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    # The reference's own contract (surf.cpp:335-342): keypoints come back to the host, descriptors are computed and STAY on
+    # the device (its *desc_addr is a device pointer that Surfor::match consumes there). Same streaming call, the wait
+    # without a descriptor destination: 0.24 MB instead of 1.5 MB per frame travel device -> host.
+    e2e_steps(3, with_desc=False)
+    barrier()
+    t4 = time.perf_counter()
+    e2e_steps(args.steps, with_desc=False)
+    torch.cuda.synchronize()
+    t5 = time.perf_counter()
+    tk = torch.tensor([t5 - t4], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+    e2e_kp = {"value": B * world * args.steps / float(tk.item()), "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
+              "d2h_bytes_per_step": int(4 * B + B * int(h_cnt.max().item()) * 48),
+              "what": "descriptors computed and left on the device, as Surfor::detectAndCompute returns them (surfd.cu:3262-3266); "
+                      "counts + keypoints to pinned host memory"}
     e2e = {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
            # counts + one strided copy per array, as wide as the batch's largest count (what sb_wait_batch_host moves)
            "d2h_bytes_per_step": int(4 * B + B * int(h_cnt.max().item()) * (48 + nf * 4)),
@@ -348,11 +364,24 @@ def run_ours(args, rank, world, local_rank, dist):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
                 "data": "synthetic", "config": workload_config(B, world),
                 "keypoints_per_frame": kp_mean, "host_numa_binding": numa,
-                "e2e": e2e, "gpu_launches": kpf * args.steps, "clocks": clocks, "roofline": roofline,
+                "e2e": e2e, "e2e_descriptors_stay_on_device": e2e_kp, "host_copy_ceiling": host_ceiling(world),
+                "gpu_launches": kpf * args.steps, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "latency": lat, "strong_scaling_configs3": strong, "configs2_4k": cfg2,
                 "configs4_stereo": cfg4, "impl": "ours"}
         emit(json.dumps(line))
     det.close()
+
+
+def host_ceiling(world):
+    """Raw pinned-copy ceiling of the 8-GPU box at this rank count, from the committed measurement (not taken in this run):
+    what `e2e` can reach at most when every rank moves one step's bytes both ways."""
+    try:
+        hj = json.load(open(os.path.join(ROOT, "profiles", "r2_host_copy_ceiling.json")))["runs"][str(world)]
+        return {"frames_per_s_both_directions": hj["both_x1"]["frames_per_s_ceiling"], "h2d_gbs_total": hj["h2d_only_x1"]["gbs_total"],
+                "d2h_gbs_total": hj["d2h_only_x1"]["gbs_total"], "both_gbs_total": hj["both_x1"]["gbs_total"],
+                "source": "committed capture profiles/r2_host_copy_ceiling.json (tools/host_copy_ceiling.py on the 8 x B200 box)"}
+    except Exception:
+        return None
 
 
 def measure_4k(sb, torch, dev, local_rank):

@@ -108,6 +108,31 @@ __device__ __forceinline__ int div_small(int a, float inv) { return __float2int_
 // consecutive words of one or two planes (4-8 sectors up to octave 2).
 __device__ __forceinline__ int phase_col(int X, int pitch) { return (X & 7) * (pitch >> 3) + (X >> 3); }
 
+// Programmatic dependent launch between the kernels of a frame: a kernel launched with launch_dep() may be placed on the SMs
+// while its predecessor in the stream is still draining; it executes pdl_wait() before its first memory access, which blocks
+// until the predecessor has completed and its writes are visible, so the data flow is that of plain stream order -- only the
+// launch latency and the ramp-up of every kernel overlap the tail of the one before (8 launches per frame: it matters for
+// the single-frame latency, not for batches). pdl_wait() is a no-op in a kernel launched without the attribute.
+// Opt-in (SURFB200_PDL=1, read once): on the B200 it made the single frame SLOWER (ctx.cpp: pdl_enabled), so by default every
+// kernel is launched plainly and pdl_wait() does nothing.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // launchers (one translation unit per stage)
 cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_pitch, int w, int h, uint8_t* d_dst,
                               size_t dst_stride, int dst_pitch, int nframes, cudaStream_t st);

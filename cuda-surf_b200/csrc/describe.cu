@@ -66,6 +66,7 @@ struct OrientSmem {
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb_point* __restrict__ points,
               long long pts_stride, const int* __restrict__ counts, int fixed_count, int* __restrict__ work) {
+    pdl_wait();
     __shared__ OrientSmem sm[kWarpsPerCta];
     __shared__ float s_lut1[83];
     __shared__ short s_tab[kOValid + 3];  // lattice index qi of the d-th point inside the circle, ascending
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
                         long long desc_stride, int* __restrict__ work) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz, O = P.orient_size;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -467,6 +469,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
                         long long desc_stride, int* __restrict__ work, const int* __restrict__ cls_idx, int* __restrict__ cls_cnt,
                         int slot0) {
+    pdl_wait();
     extern __shared__ __align__(16) float smem[];
     const int NF = P.nfeatures, W = P.desc_wsz;
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -744,20 +747,22 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     if (ctas > need) ctas = need;
     const dim3 grid(ctas, nframes), block(kWarpsPerCta * 32);
     // (the orientation pass has its own counters: d_work_orient)
-    if (!P.upright) orient_kernel<<<grid, block, 0, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_work_orient);
+    cudaError_t e = cudaSuccess;
+    if (!P.upright) e = launch_dep(orient_kernel, grid, block, 0, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_work_orient);
+    if (e != cudaSuccess) return e;
     if (P.upright) {
         const size_t smem = ((size_t)kWarpsPerCta * (P.desc_wsz * P.orient_size + P.desc_wsz) * kTS + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
         if (P.orient_size == 4) {
             cudaFuncSetAttribute(describe_upright_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            describe_upright_kernel<4><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, cls_idx, cls_cnt, aux.slot0);
+            return launch_dep(describe_upright_kernel<4>, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, cls_idx, cls_cnt, aux.slot0);
         } else {
             cudaFuncSetAttribute(describe_upright_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            describe_upright_kernel<8><<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, nullptr, nullptr, 0);
+            return launch_dep(describe_upright_kernel<8>, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, (const int*)nullptr, (int*)nullptr, 0);
         }
     } else {
         const size_t smem = ((size_t)kWarpsPerCta * (2 * kRotRows + 32) + (size_t)kWarpsPerCta * (P.nfeatures + 8) * 32 + 40) * sizeof(float);
         cudaFuncSetAttribute(describe_rotated_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        describe_rotated_kernel<<<grid, block, smem, st>>>(P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work);
+        return launch_dep(describe_rotated_kernel, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work);
     }
     return cudaGetLastError();
 }

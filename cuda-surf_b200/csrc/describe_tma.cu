@@ -116,6 +116,7 @@ struct Sweep {
 __global__ void classify_kernel(const __grid_constant__ PipeP P, const sb_point* __restrict__ points, long long pts_stride,
                                 const int* __restrict__ counts, int fixed_count, int* __restrict__ cls_idx,
                                 int* __restrict__ cls_cnt, int slot0, int dbg_mask) {
+    pdl_wait();
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
     const sb_point* pts = points + (size_t)f * pts_stride;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(32)
 describe_upright_tma_kernel(const __grid_constant__ PipeP P, const void* __restrict__ maps, const sb_point* __restrict__ points,
                             long long pts_stride, const int* __restrict__ cls_idx, const int* __restrict__ cls_cnt, int slot0,
                             float* __restrict__ desc, long long desc_stride) {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.y, lane = threadIdx.x;
     const uint32_t raw_sa = smem_u32(smem_raw);
@@ -452,18 +454,17 @@ cudaError_t launch_describe_tma(const PipeP& P, int nframes, const DescAux& aux,
                                 cudaStream_t st) {
     const int maxn = fixed_count >= 0 ? fixed_count : P.max_pts;
     static const int dbg_mask = getenv("SB_CLS_MASK") ? atoi(getenv("SB_CLS_MASK")) : -1;  // measurement only: skips the TMA kernel
-    classify_kernel<<<dim3(max(1, min(16, (maxn + 255) / 256)), nframes), 256, 0, st>>>(P, d_points, pts_stride, d_counts, fixed_count,
-                                                                                      aux.cls_idx, aux.cls_cnt, aux.slot0, dbg_mask);
-    if (dbg_mask >= 0) return cudaGetLastError();
+    cudaError_t e = launch_dep(classify_kernel, dim3(max(1, min(16, (maxn + 255) / 256)), nframes), dim3(256), 0, st, P, d_points, pts_stride,
+                               d_counts, fixed_count, aux.cls_idx, aux.cls_cnt, aux.slot0, dbg_mask);
+    if (e != cudaSuccess || dbg_mask >= 0) return e;
     const int smem = kFSmem + 512;
-    cudaError_t e = cudaFuncSetAttribute(describe_upright_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(describe_upright_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const int resident = sm_count * (int)((227 * 1024) / (smem + 1024));
     int warps = max(1, resident / nframes);
     if (warps > maxn) warps = maxn;
-    describe_upright_tma_kernel<<<dim3(warps, nframes), 32, smem, st>>>(P, aux.maps, d_points, pts_stride, aux.cls_idx, aux.cls_cnt,
-                                                                        aux.slot0, d_desc, desc_stride);
-    return cudaGetLastError();
+    return launch_dep(describe_upright_tma_kernel, dim3(warps, nframes), dim3(32), smem, st, P, aux.maps, d_points, pts_stride,
+                      (const int*)aux.cls_idx, (const int*)aux.cls_cnt, aux.slot0, d_desc, desc_stride);
 }
 
 }  // namespace sb

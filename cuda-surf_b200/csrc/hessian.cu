@@ -88,6 +88,7 @@ __device__ __forceinline__ float hessian_response(const int* __restrict__ row, c
 __global__ void __launch_bounds__(256, 4)
 hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Iphase, float* __restrict__ Rbase, int first_tile,
                int nlayers) {
+    pdl_wait();
     const int f = blockIdx.y;
     // nlayers > 0: one CTA per (tile, layer), the layer fastest; nlayers == 0: one CTA per tile loops over its layers, which
     // share the tile's patch of the integral in L1 (used for batches, where there are CTAs enough without the split)
@@ -207,6 +208,7 @@ __device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict
 // grid (tiles_x * tiles_y, nframes), 256 threads, 24 KB static shared memory
 __global__ void __launch_bounds__(256, 4)
 hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int tiles_x) {
+    pdl_wait();
     __shared__ __align__(16) int patch[4 * kPlane + 16];
     const int f = blockIdx.y;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
@@ -261,7 +263,8 @@ cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, c
     int first_tile = 0;
     if (fast0) {
         const int tiles_x = (q0.sw + kTW - 1) / kTW, tiles_y = (q0.sh + kTH - 1) / kTH;
-        hessian_o0_kernel<<<dim3(tiles_x * tiles_y, nframes), 256, 0, st>>>(P, d_integral, d_resp, tiles_x);
+        const cudaError_t e = launch_dep(hessian_o0_kernel, dim3(tiles_x * tiles_y, nframes), dim3(256), 0, st, P, d_integral, d_resp, tiles_x);
+        if (e != cudaSuccess) return e;
         first_tile = P.noctaves > 1 ? P.oct[1].hess_tile0 : P.hess_tiles;
     }
     if (P.hess_tiles - first_tile > 0) {
@@ -271,7 +274,7 @@ cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, c
         // (grid.y is the frame: the integral / response slots are indexed by blockIdx.y in every kernel)
         const bool fuse = nframes >= 16;
         const dim3 grid((P.hess_tiles - first_tile) * (fuse ? 1 : maxnl), nframes), block(32, 8);
-        hessian_kernel<<<grid, block, 0, st>>>(P, d_integral_ph, d_resp, first_tile, fuse ? 0 : maxnl);
+        return launch_dep(hessian_kernel, grid, block, 0, st, P, d_integral_ph, d_resp, first_tile, fuse ? 0 : maxnl);
     }
     return cudaGetLastError();
 }

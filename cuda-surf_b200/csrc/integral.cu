@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 6)
 integral_scan(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs, size_t image_stride, int pitch,
               const int* __restrict__ T, const int* __restrict__ R, const int* __restrict__ TT, int* __restrict__ Iout,
               int* __restrict__ Iph) {
+    pdl_wait();
     __shared__ __align__(16) int tile[kBand][kChunk];
     __shared__ int s_rowbase[kBand];
     __shared__ int s_offw[8];
@@ -299,10 +300,10 @@ cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t imag
     const bool aligned = (pitch % 8 == 0) && (image_stride % 8 == 0) && ((uintptr_t)d_images % 8 == 0);
     if (aligned) {
         integral_reduce<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
-        integral_scan<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
+        return launch_dep(integral_scan<true>, grid, block, 0, st, P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
     } else {
         integral_reduce<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
-        integral_scan<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
+        return launch_dep(integral_scan<false>, grid, block, 0, st, P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
     }
     return cudaGetLastError();
 }

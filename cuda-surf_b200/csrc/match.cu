@@ -571,13 +571,16 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     }
     ws.map_nf = NF;
     // per device (a process may hold contexts on several GPUs), so set on every launch
-    static const bool use_pdl = !getenv("SB_MATCH_PDL") || atoi(getenv("SB_MATCH_PDL")) != 0;
+    static const int use_pdl = getenv("SB_MATCH_PDL") ? atoi(getenv("SB_MATCH_PDL")) : 2;  // 0 off, 1 both, 2 mma only
     static const bool use_keys = !getenv("SB_MATCH_KEYS") || atoi(getenv("SB_MATCH_KEYS")) != 0;
     if ((e = cudaFuncSetAttribute(match_mma<NF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(match_mma<NF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
-    // match_mma and match_final are programmatic dependents of their predecessor: their CTAs are placed and run their
-    // prologue (barrier set-up, tensor-memory allocation) while it is still running, and wait at griddepcontrol.wait
-    // before they touch its output -- the three launches cost one ramp-up instead of three.
+    // match_mma is a programmatic dependent of match_prep: its CTAs are placed and run their prologue (barrier set-up,
+    // tensor-memory allocation) while match_prep is still running, and the producer thread waits at griddepcontrol.wait
+    // before the first TMA touches match_prep's output. match_final is launched normally: as a programmatic dependent its
+    // 685 CTAs sat on the SMs beside match_mma's and the three kernels took 24.7 us instead of 20.5 (B200, CUDA graph of
+    // the three launches, 2739 x 3443; no dependent launch at all: 20.8). SB_MATCH_PDL / SB_MATCH_KEYS are measurement
+    // switches.
     cudaLaunchAttribute pdl[1];
     pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pdl[0].val.programmaticStreamSerializationAllowed = 1;
@@ -588,6 +591,7 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     else e = cudaLaunchKernelEx(&cfg, match_mma<NF, false>, mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
     if (e != cudaSuccess) return e;
     cfg.gridDim = dim3((n1 + 3) / 4); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0;
+    cfg.numAttrs = use_pdl == 1 ? 1 : 0;
     if ((e = cudaLaunchKernelEx(&cfg, match_final<NF>, d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit, n1pad)) != cudaSuccess) return e;
     return cudaGetLastError();
 }

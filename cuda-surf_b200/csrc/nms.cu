@@ -116,6 +116,7 @@ constexpr int kCandShiftS = 26, kCandShiftO = 29;  // packed candidate: c [0,13)
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase, unsigned* __restrict__ cand,
                 int* __restrict__ cand_count, int cand_cap) {
+    pdl_wait();
     const int f = blockIdx.y;
     const int tile = blockIdx.x;
     int o = 0;
@@ -218,6 +219,7 @@ constexpr int kNmsR = 20, kNmsC = 72;  // staged rows / padded columns: dm <= 2
 __global__ void __launch_bounds__(256, 4)
 nms_scan_tile_kernel(const __grid_constant__ PipeP P, const float* __restrict__ Rbase, unsigned* __restrict__ cand,
                      int* __restrict__ cand_count, int cand_cap) {
+    pdl_wait();
     __shared__ __align__(16) float blk[5][kNmsR][kNmsC];
     const int f = blockIdx.y;
     int lt = blockIdx.x, o = 0;
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(128)
 nms_refine_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const float* __restrict__ Rbase,
                   const unsigned* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
                   sb_point* __restrict__ points, int* __restrict__ counts) {
+    pdl_wait();
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int ncand = min(cand_count[f], cand_cap);
     const int ms = P.max_scale;
@@ -416,6 +419,7 @@ nms_refine_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
 // Clamp the keypoint counts to the capacity and re-arm the candidate counters for the next call (they are zero after
 // sb_create, and every pass leaves them zero again: no memset in the per-frame sequence).
 __global__ void clamp_counts_kernel(int* counts, int n, int max_pts, int* cand_count, int* work, int* work2, int* cls_cnt) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         counts[i] = min(counts[i], max_pts); cand_count[i] = 0; work[i] = 0; work2[i] = 0;
@@ -426,6 +430,7 @@ __global__ void clamp_counts_kernel(int* counts, int n, int max_pts, int* cand_c
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
                        int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st) {
     // standard octaves (5 layers, the two cell lattices at most 2 samples apart): shared-memory scan, one CTA per tile
+    cudaError_t e = cudaSuccess;
     bool tiled = P.max_scale == 5;
     int ctiles = 0;
     for (int o = 0; o < P.noctaves; o++) {
@@ -434,18 +439,17 @@ cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const
         ctiles += q.nms_tx * q.nms_ty;
     }
     if (tiled)
-        nms_scan_tile_kernel<<<dim3(ctiles, nframes), dim3(32, 8), 0, st>>>(P, d_resp, d_cand, d_cand_count, cand_cap);
+        e = launch_dep(nms_scan_tile_kernel, dim3(ctiles, nframes), dim3(32, 8), 0, st, P, d_resp, d_cand, d_cand_count, cand_cap);
     else
-        nms_scan_kernel<<<dim3(P.nms_tiles, nframes), dim3(32, 8), 0, st>>>(P, d_resp, d_cand, d_cand_count, cand_cap);
+        e = launch_dep(nms_scan_kernel, dim3(P.nms_tiles, nframes), dim3(32, 8), 0, st, P, d_resp, d_cand, d_cand_count, cand_cap);
     // ~5 k candidates per 1080p frame: 48 CTAs of 128 threads cover them in one pass, more are looped over
-    nms_refine_kernel<<<dim3(48, nframes), 128, 0, st>>>(P, d_integral, d_resp, d_cand, d_cand_count, cand_cap, d_points, d_counts);
-    return cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_dep(nms_refine_kernel, dim3(48, nframes), dim3(128), 0, st, P, d_integral, d_resp, d_cand, d_cand_count, cand_cap, d_points, d_counts);
 }
 
 cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, int* d_work_orient,
                                 int* d_cls_cnt, cudaStream_t st) {
-    clamp_counts_kernel<<<(nframes + 255) / 256, 256, 0, st>>>(d_counts, nframes, max_pts, d_cand_count, d_work, d_work_orient, d_cls_cnt);
-    return cudaGetLastError();
+    return launch_dep(clamp_counts_kernel, dim3((nframes + 255) / 256), dim3(256), 0, st, d_counts, nframes, max_pts, d_cand_count, d_work, d_work_orient, d_cls_cnt);
 }
 
 }  // namespace sb

@@ -91,6 +91,18 @@ def rotated_bar(ref, img, rpts, rdesc, pts, desc, max_pts, nruns=2):
     return spread, best[ok0]
 
 
+
+def assert_ambiguity(got, want, what):
+    """ambiguity = second / best, exact except where a group's second and third candidate are closer than the ranking
+    resolution of the tensor-core pass (3e-5: split-bf16 product, packed keys): the exact re-score then sees the third and
+    the ratio moves by < 1e-4. At most two such rows per match are tolerated (offline estimate: one row in ~10 matches of
+    5 k x 5 k descriptors); everything else must agree to 1e-6."""
+    d = np.abs(got["ambiguity"] - want["ambiguity"])
+    near = np.nonzero(d > 1e-6)[0]
+    assert len(near) <= 2 and (len(d) == 0 or d.max() <= 1e-4), f"{what}: ambiguity differs in rows {near[:10]} by up to {d.max():.3e}"
+    return near, d
+
+
 def assert_resp_close(got, want, what):
     assert got.shape == want.shape, what
     if np.array_equal(got, want):
@@ -272,7 +284,7 @@ def test_match_vs_reference():
     ref.close()
     assert np.array_equal(got["match"], want["match"])
     assert np.array_equal(got["score"], want["score"])
-    assert np.allclose(got["ambiguity"], want["ambiguity"], rtol=0, atol=1e-6)
+    assert_ambiguity(got, want, "bundled pair")
     assert np.array_equal(got["match_x"], want["match_x"]) and np.array_equal(got["match_y"], want["match_y"])
     # host copy of the five match fields (surf.cpp:421-425)
     assert np.array_equal(d1.h_data["match"][: d1.num_pts], got["match"])
@@ -303,7 +315,7 @@ def test_match_vs_oracle_and_tail_rule():
         assert np.array_equal(got["match"], want["match"]), (n1, n2)
         assert (got["match"] < n2 - n2 % 32).all()  # the last n2 % 32 descriptors are never candidates
         assert np.array_equal(got["score"], want["score"])
-        assert np.allclose(got["ambiguity"], want["ambiguity"], atol=1e-6)
+        assert_ambiguity(got, want, f"{n1} x {n2}")
 
 
 @pytest.mark.parametrize("nf,n1,n2", [(64, 2739, 3443), (128, 700, 1500), (64, 128, 256), (128, 1, 40)])
@@ -600,7 +612,7 @@ def test_init_argument_variants_vs_oracle(kw):
         want = ol.match(got, f1[: d1.num_pts].cpu().numpy(), d2.host_points(), f2[: d2.num_pts].cpu().numpy())
         assert np.array_equal(got["match"], want["match"])
         assert np.allclose(got["score"], want["score"], rtol=0, atol=1e-6)
-        assert np.allclose(got["ambiguity"], want["ambiguity"], rtol=0, atol=1e-5)
+        assert_ambiguity(got, want, "init variants")
 
 
 # ---------------------------------------------------------------------------------------- full-size parity vs the reference
@@ -667,10 +679,8 @@ def test_stereo_1080p_match_vs_reference(report):
         # the tensor-core pass ranks highest (2e-5 resolution: split-bf16 product); when a group's second and third
         # candidate are closer than that, the exact re-score may see the third: |delta ambiguity| <= 1e-4 then. Such rows
         # are rare (offline estimate: one row in ~10 pairs), listed in the parity report, and bounded here.
-        damb = np.abs(got["ambiguity"] - want["ambiguity"])
-        near = np.nonzero(damb > 1e-6)[0]
+        near, damb = assert_ambiguity(got, want, f"stereo pair {p}")
         report(**{"case": f"stereo pair {p} 1080p ambiguity", "rows_over_1e-6": [int(i) for i in near[:20]], "max_abs_diff": float(damb.max())})
-        assert len(near) <= 2 and damb.max() <= 1e-4, f"pair {p}: ambiguity differs in rows {near[:10]} by up to {damb.max():.3e}"
         assert np.array_equal(got["match_x"], want["match_x"]) and np.array_equal(got["match_y"], want["match_y"])
     ref.close()
 
