@@ -70,6 +70,7 @@ def lib():
         L.sb_detect_and_compute.argtypes = [vp, vp, i, i, i, vp, vp, i, C.POINTER(i), C.POINTER(vp), i]
         L.sb_match.argtypes = [vp, vp, vp, i, vp, vp, i, vp]
         L.sb_match_async.argtypes = [vp, vp, i, vp, vp, i, vp, vp]
+        L.sb_match_pairs_async.argtypes = [vp, vp, C.c_longlong, vp, vp, C.c_longlong, i, vp, i, vp]
         L.sb_match_filter.argtypes = [vp, vp, i, vp, i, f, i, vp, vp, i, C.POINTER(i)]
         L.sb_detect_batch_async.argtypes = [vp, vp, sz, i, i, vp, vp, vp, vp]
         L.sb_detect_batch_host.argtypes = [vp, vp, i, vp, vp, vp]
@@ -81,7 +82,7 @@ def lib():
         L.sb_get_response.argtypes = [vp, i, vp]
         L.sb_describe.argtypes = [vp, i, vp, i, vp]
         L.sb_synth_frame.argtypes = [vp, i, i, i, C.c_uint64, i, i, C.c_uint64]
-        for name in ("sb_create", "sb_get_info", "sb_detect_and_compute", "sb_match", "sb_match_async", "sb_match_filter", "sb_detect_batch_async",
+        for name in ("sb_create", "sb_get_info", "sb_detect_and_compute", "sb_match", "sb_match_async", "sb_match_pairs_async", "sb_match_filter", "sb_detect_batch_async",
                      "sb_detect_batch_host", "sb_submit_batch_host", "sb_wait_batch_host", "sb_detect_batch_profile", "sb_sync", "sb_get_integral", "sb_get_response", "sb_describe",
                      "sb_synth_frame"):
             getattr(L, name).restype = i

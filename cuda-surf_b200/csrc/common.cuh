@@ -169,10 +169,13 @@ struct MatchScratch {
     // sets of the same padded sizes again -- a video stream -- does not pay cuTensorMapEncodeTiled twice per call
     alignas(64) unsigned char map_a[128], map_b[128];
     const void* map_a_base = nullptr; const void* map_b_base = nullptr;
-    int map_a_rows = 0, map_b_rows = 0, map_nf = 0;
+    int map_a_rows = 0, map_b_rows = 0, map_nf = 0, map_pairs = 0;
 };
 cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
                          int nfeatures, MatchScratch& ws, int sm_count, cudaStream_t st);
+// pair z: frame d_pairs[2z] against frame d_pairs[2z+1] (d_pairs == nullptr: 2z, 2z+1) of one detect batch, counts on the device
+cudaError_t launch_match_batch(sb_point* d_pts, long long pts_stride, const int* d_counts, const float* d_desc, long long desc_stride,
+                               int npairs, const int* d_pairs, int bound, int nfeatures, MatchScratch& ws, int sm_count, cudaStream_t st);
 void free_match_scratch(MatchScratch& ws);
 cudaError_t launch_match_filter(const sb_point* d_pts1, int n1, const sb_point* d_pts2, int n2, float max_ambiguity, int flags,
                                 sb_pair* d_pairs, int cap, int* d_count, cudaStream_t st);

@@ -715,6 +715,21 @@ extern "C" int sb_match_async(sb_ctx* ctx, sb_point* d_pts1, int n1, const float
     return SB_OK;
 }
 
+extern "C" int sb_match_pairs_async(sb_ctx* ctx, sb_point* d_points, long long pts_stride, const int* d_counts, const float* d_desc,
+                                    long long desc_stride, int npairs, const int* d_pairs, int bound, void* stream) {
+    if (!ctx) return SB_ERR_INVALID;
+    if (npairs < 0 || bound < 0 || (npairs > 0 && (!d_points || !d_counts || !d_desc)) || pts_stride < bound ||
+        desc_stride < (long long)bound * ctx->P.nfeatures)
+        return fail(ctx, SB_ERR_INVALID, "sb_match_pairs_async: bad argument");
+    if (ctx->P.nfeatures != 64 && ctx->P.nfeatures != 128)
+        return fail(ctx, SB_ERR_INVALID, "sb_match_pairs_async: 64- and 128-d descriptors only (use sb_match per pair)");
+    if (npairs == 0 || bound == 0) return SB_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(launch_match_batch(d_points, pts_stride, d_counts, d_desc, desc_stride, npairs, d_pairs, bound, ctx->P.nfeatures, ctx->match_ws,
+                          ctx->sm_count, (cudaStream_t)stream));
+    return SB_OK;
+}
+
 extern "C" int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const float* d_feat1,
                         const sb_point* d_pts2, int n2, const float* d_feat2) {
     if (!ctx) return SB_ERR_INVALID;

@@ -463,7 +463,8 @@ constexpr int kTS = 36;
 struct TrueT { static constexpr bool value = true; };
 struct FalseT { static constexpr bool value = false; };
 
-template <int O>
+// LIST: the keypoints come from the class list the TMA path left (describe_tma.cu); false compiles the list handling away
+template <int O, bool LIST>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 5)
 describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const sb_point* __restrict__ points,
                         long long pts_stride, const int* __restrict__ counts, int fixed_count, float* __restrict__ desc,
@@ -485,9 +486,9 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     float* Wc = T + W * O * kTS;
     const unsigned lut_sa = (unsigned)__cvta_generic_to_shared(s_lut2);
     // with a class list (describe_tma.cu) this kernel takes the keypoints the TMA path left: list position -> keypoint
-    const int* list = cls_idx ? cls_idx + ((size_t)(slot0 + f) * 2 + 1) * P.max_pts : nullptr;
-    int* wk = cls_cnt ? cls_cnt + (slot0 + f) * 4 + 3 : work + f;  // this frame's work counter
-    const int n = list ? cls_cnt[(slot0 + f) * 4 + 1] : (fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts));
+    const int* list = LIST ? cls_idx + ((size_t)(slot0 + f) * 2 + 1) * P.max_pts : nullptr;
+    int* wk = LIST ? cls_cnt + (slot0 + f) * 4 + 3 : work + f;  // this frame's work counter
+    const int n = LIST ? cls_cnt[(slot0 + f) * 4 + 1] : (fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts));
     const int ip = P.ip;
     const int* I = Ibase + (size_t)f * P.istride + ip;
     const sb_point* pts = points + (size_t)f * pts_stride;
@@ -498,7 +499,7 @@ describe_upright_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     // a warp's first keypoint is fixed, the following ones come from a per-frame counter (zero on entry): keypoints cost
     // 2 or 3 passes, and with one or two per warp (single frame) a static split left the machine waiting for the unlucky warps
     for (int pk = blockIdx.x * kWarpsPerCta + warp; pk < n;) {
-        const int pi = list ? list[pk] : pk;
+        const int pi = LIST ? list[pk] : pk;
         const float x = pts[pi].x, y = pts[pi].y;
         const KpGeom kg = kp_geom(x, y, pts[pi].scale, W, P.mag_factor, P.doubled);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};  // descriptor elements lane, lane+32, ... (un-normalised)
@@ -753,11 +754,15 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     if (P.upright) {
         const size_t smem = ((size_t)kWarpsPerCta * (P.desc_wsz * P.orient_size + P.desc_wsz) * kTS + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
         if (P.orient_size == 4) {
-            cudaFuncSetAttribute(describe_upright_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            return launch_dep(describe_upright_kernel<4>, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, cls_idx, cls_cnt, aux.slot0);
+            if (tma) {
+                cudaFuncSetAttribute(describe_upright_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                return launch_dep(describe_upright_kernel<4, true>, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, cls_idx, cls_cnt, aux.slot0);
+            }
+            cudaFuncSetAttribute(describe_upright_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            return launch_dep(describe_upright_kernel<4, false>, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, (const int*)nullptr, (int*)nullptr, 0);
         } else {
-            cudaFuncSetAttribute(describe_upright_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            return launch_dep(describe_upright_kernel<8>, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, (const int*)nullptr, (int*)nullptr, 0);
+            cudaFuncSetAttribute(describe_upright_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            return launch_dep(describe_upright_kernel<8, false>, grid, block, smem, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_desc, desc_stride, d_work, (const int*)nullptr, (int*)nullptr, 0);
         }
     } else {
         const size_t smem = ((size_t)kWarpsPerCta * (2 * kRotRows + 32) + (size_t)kWarpsPerCta * (P.nfeatures + 8) * 32 + 40) * sizeof(float);

@@ -25,6 +25,7 @@
 //                   So score / match are those of the reference unless two candidates of one group
 //                   are closer than the split-bf16 error to the group's second place.
 #include <cuda.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <cuda_bf16.h>
 
@@ -40,15 +41,22 @@ constexpr int kSwizzleRow = 128;  // bytes per operand row chunk (64 bf16) == on
 constexpr int kStages = 2;      // B' tiles in flight == TMEM accumulators
 constexpr int kEpiWarps = 8;    // epilogue warps; warp kEpiWarps is the producer (TMA + MMA issue)
 
-template <int NF> struct MatchCfg {
+// MB = row blocks of A' per CTA: every B' tile that arrives in shared memory is multiplied with MB x 128 rows. The
+// batched form uses MB = 2 for 64-d descriptors: with one row block a CTA streamed 48 KB of B' per 128 x 128 x 192 tile
+// product, 1248 CTAs pulled 2.3 GB through L2 for 32 pairs and the kernel ran at the L2 -> SM bandwidth (ncu: 414 us,
+// tensor pipe 38 % active).
+template <int NF, int MB = 1> struct MatchCfg {
     static constexpr int KCH = 3 * NF / 64;            // 64-element K chunks of the split operands
     static constexpr int KTOT = 3 * NF;                // K of the tensor-core GEMM
     static constexpr int BN = NF == 64 ? 128 : 64;     // columns (descriptors of set 2) per tile: two stages must fit
-    static constexpr int A_BYTES = KCH * kBM * kSwizzleRow;
+    static constexpr int A_BYTES = KCH * kBM * kSwizzleRow;   // one row block
     static constexpr int B_BYTES = KCH * BN * kSwizzleRow;
-    static constexpr int XCHG_BYTES = kBM * 8 * 16;  // top-2 of the upper column half, handed to the lower half's warps
-    static constexpr int SMEM = A_BYTES + kStages * B_BYTES + XCHG_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
-    static constexpr int TMEM_COLS = kStages * BN;     // 256 / 128: a power of two >= 32
+    static constexpr int XCHG_BYTES = kBM * 8 * 16;  // per row block: top-2 of the upper column half, handed to the lower half's warps
+    // (the exchange buffers reuse the B' stages: every tile has been multiplied when the first epilogue warp gets there)
+    static_assert(MB * XCHG_BYTES <= kStages * B_BYTES, "exchange buffers alias the B' stages");
+    static constexpr int SMEM = MB * A_BYTES + kStages * B_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
+    static constexpr int TMEM_COLS = kStages * MB * BN;     // a power of two >= 32, <= 512
+    static constexpr int THREADS = (kEpiWarps * MB + 1) * 32;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,20 +129,58 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 
+// Batched form (sb_match_pairs_async): pair z of the launch matches frame pairs[z].x against frame pairs[z].y of one
+// detect batch, with the keypoint counts read ON THE DEVICE (no host round trip between detection and matching, and one
+// launch sequence for all pairs instead of three launches per pair). counts == nullptr: the single-pair call, every
+// per-pair quantity comes from the kernel arguments as before.
+struct MatchBatch {
+    const int* counts = nullptr;   // [frames]
+    const int2* pairs = nullptr;   // [npairs]; nullptr: (2z, 2z + 1)
+    sb_point* pts = nullptr;       // [frame][pts_stride]
+    const float* desc = nullptr;   // [frame][desc_stride] floats
+    long long pts_stride = 0, desc_stride = 0;
+    int bound = 0;                 // counts are clamped to this; rows_cap = its multiple of 128 (rows per pair in the scratch)
+    int rows_cap = 0;
+    int nsplit = 1;
+};
+__device__ __forceinline__ int2 batch_pair(const MatchBatch& mb, int z) { return mb.pairs ? mb.pairs[z] : make_int2(2 * z, 2 * z + 1); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------------------- 1. operand split
 // rows >= nvalid are zero (padding of A', non-candidates of B'); out: [rows_pad][3*NF] bf16. One launch for both sets.
 template <int NF>
 __global__ void match_prep(const float* __restrict__ fa, int na, int na_pad, __nv_bfloat16* __restrict__ outa,
-                           const float* __restrict__ fb, int nb, int nb_pad, __nv_bfloat16* __restrict__ outb) {
+                           const float* __restrict__ fb, int nb, int nb_pad, __nv_bfloat16* __restrict__ outb,
+                           const __grid_constant__ MatchBatch mb) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // match_mma's prologue overlaps this kernel
     // a thread converts 8 consecutive elements of a row: two 128-bit loads, three 128-bit stores (hi, and lo / hi again)
     constexpr int PER = NF / 8;
+    constexpr int BN = NF == 64 ? 128 : 64;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     int row = t / PER;
     const int d = (t - row * PER) * 8;
-    const bool is_b = row >= na_pad;
-    if (is_b) row -= na_pad;
-    if (is_b && row >= nb_pad) return;
+    bool is_b = row >= na_pad;
+    if (mb.counts) {
+        // blockIdx.y = 2 * pair + role; rows [0, rows_cap) of the pair's slot: valid rows, then zeros up to the padded size
+        const int z = blockIdx.y >> 1;
+        is_b = blockIdx.y & 1;
+        const int2 pr = batch_pair(mb, z);
+        const int fr = is_b ? pr.y : pr.x;
+        const int n = min(mb.counts[fr], mb.bound);
+        if (is_b) { nb = n - (n & 31); nb_pad = max((nb + BN - 1) / BN, 1) * BN; }
+        else { na = n; na_pad = (n + kBM - 1) / kBM * kBM; }
+        if (row >= (is_b ? nb_pad : na_pad)) return;
+        fa = fb = mb.desc + (size_t)fr * mb.desc_stride;
+        outa += (size_t)z * mb.rows_cap * (3 * NF);
+        outb += (size_t)z * mb.rows_cap * (3 * NF);
+    } else {
+        if (is_b) row -= na_pad;
+        if (is_b && row >= nb_pad) return;
+    }
     const float* f = is_b ? fb : fa;
     const int nvalid = is_b ? nb : na;
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -164,24 +210,36 @@ struct __align__(16) Top2 { float mx, sc; int imx, isc; };  // 16 bytes, moved a
 // epilogue of tile i-1 out of TMEM. Per stage three mbarriers: `full` (TMA landed), `mma` (tcgen05.commit: accumulator
 // ready, operands consumed), `free` (the eight epilogue warps have read the accumulator). Round-1 v1 did load -> MMA ->
 // epilogue strictly one after the other (ncu: tensor pipe active 12.5 % of the kernel).
-template <int NF, bool KEYS>
-__global__ void __launch_bounds__((kEpiWarps + 1) * 32, 1)
+template <int NF, bool KEYS, int MB>
+__global__ void __launch_bounds__((kEpiWarps * MB + 1) * 32, 1)
 match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles, int tiles_per_split,
-          int n1pad, Top2* __restrict__ part) {
-    using Cfg = MatchCfg<NF>;
+          int n1pad, Top2* __restrict__ part, const __grid_constant__ MatchBatch mb) {
+    using Cfg = MatchCfg<NF, MB>;
     constexpr int BN = Cfg::BN, KCH = Cfg::KCH;
+    const int zpair = blockIdx.z;
+    if (mb.counts) {
+        // per-pair geometry from the device-side counts; row blocks past the pair's rows leave at once
+        const int2 pr = batch_pair(mb, zpair);
+        const int n1 = min(mb.counts[pr.x], mb.bound), n2 = min(mb.counts[pr.y], mb.bound);
+        if ((int)blockIdx.x * MB * kBM >= n1) return;
+        const int ncand = n2 - (n2 & 31);
+        ntiles = (ncand + BN - 1) / BN;
+        tiles_per_split = (ntiles + mb.nsplit - 1) / mb.nsplit;
+        n1pad = mb.rows_cap;
+        part += (size_t)zpair * mb.nsplit * mb.rows_cap * 8;
+    }
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;                    // KCH chunks of 128 rows x 128 B
-    uint8_t* sB = smem + Cfg::A_BYTES;     // kStages x (KCH chunks of BN rows x 128 B)
-    float4* xchg = reinterpret_cast<float4*>(smem + Cfg::A_BYTES + kStages * Cfg::B_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + kStages * Cfg::B_BYTES + Cfg::XCHG_BYTES);
+    uint8_t* sA = smem;                         // MB x (KCH chunks of 128 rows x 128 B)
+    uint8_t* sB = smem + MB * Cfg::A_BYTES;     // kStages x (KCH chunks of BN rows x 128 B)
+    float4* xchg = reinterpret_cast<float4*>(sB);  // after the last tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MB * Cfg::A_BYTES + kStages * Cfg::B_BYTES);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // match_final's CTAs may take their places now
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rb = blockIdx.x, split = blockIdx.y;
+    const int rb0 = blockIdx.x * MB, split = blockIdx.y;
     const int t0 = split * tiles_per_split, t1 = min(ntiles, t0 + tiles_per_split);
-    const int n = t1 - t0;
+    const int n = max(t1 - t0, 0);
     auto bar_full = [&](int st) { return smem_u32(&bars[st]); };
     auto bar_mma = [&](int st) { return smem_u32(&bars[kStages + st]); };
     auto bar_free = [&](int st) { return smem_u32(&bars[2 * kStages + st]); };
@@ -189,23 +247,26 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     constexpr uint32_t idesc = umma_idesc(kBM, BN);
     auto issue_tma = [&](int i) {  // tile t0+i into stage i % kStages (and, once, the CTA's rows of A')
         const int st = i % kStages;
-        mbar_expect_tx(bar_full(st), Cfg::B_BYTES + (i == 0 ? Cfg::A_BYTES : 0));
+        mbar_expect_tx(bar_full(st), Cfg::B_BYTES + (i == 0 ? MB * Cfg::A_BYTES : 0));
+        // (the maps are [pair][row][k]: the single-pair call has one pair; rows past the operand buffer arrive as zeros)
         if (i == 0)
-            for (int c = 0; c < KCH; c++) tma_load_2d(smem_u32(sA + c * kBM * kSwizzleRow), &mapA, bar_full(st), c * 64, rb * kBM);
+            for (int m = 0; m < MB; m++)
+                for (int c = 0; c < KCH; c++)
+                    tma_load_3d(smem_u32(sA + m * Cfg::A_BYTES + c * kBM * kSwizzleRow), &mapA, bar_full(st), c * 64, (rb0 + m) * kBM, zpair);
         for (int c = 0; c < KCH; c++)
-            tma_load_2d(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow), &mapB, bar_full(st), c * 64, (t0 + i) * BN);
+            tma_load_3d(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow), &mapB, bar_full(st), c * 64, (t0 + i) * BN, zpair);
     };
-    if (tid == kEpiWarps * 32) {
+    if (tid == kEpiWarps * MB * 32) {
         // the producer thread arms the barriers itself and starts the first loads at once: they fly while warp 1 allocates
         // tensor memory and the CTA meets at the barrier below
-        for (int st = 0; st < kStages; st++) { mbar_init(bar_full(st), 1); mbar_init(bar_mma(st), 1); mbar_init(bar_free(st), kEpiWarps); }
+        for (int st = 0; st < kStages; st++) { mbar_init(bar_full(st), 1); mbar_init(bar_mma(st), 1); mbar_init(bar_free(st), kEpiWarps * MB); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // (programmatic dependent launch: everything above overlaps match_prep; its output is first touched here)
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (n > 0) issue_tma(0);
     }
-    if (warp == 1) {  // TMEM: kStages accumulators of BN fp32 columns x 128 lanes
+    if (warp == 1) {  // TMEM: kStages x MB accumulators of BN fp32 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -214,7 +275,7 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == kEpiWarps) {
+    if (warp == kEpiWarps * MB) {
         // ------------------------------------------------------------------ producer: one thread
         if (lane == 0 && n > 0) {
             for (int i = 0; i < n; i++) {
@@ -227,21 +288,23 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 mbar_wait(bar_full(st), use & 1);
                 if (use >= 1) mbar_wait(bar_free(st), (use - 1) & 1);  // the epilogue of tile i-kStages has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // D[128 x BN] = sum over K chunks and 16-element K steps
-                for (int c = 0; c < KCH; c++) {
-                    const uint64_t da = umma_desc(smem_u32(sA + c * kBM * kSwizzleRow));
-                    const uint64_t db = umma_desc(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow));
+                // D_m[128 x BN] = sum over K chunks and 16-element K steps, for each of the CTA's row blocks
+                for (int m = 0; m < MB; m++)
+                    for (int c = 0; c < KCH; c++) {
+                        const uint64_t da = umma_desc(smem_u32(sA + m * Cfg::A_BYTES + c * kBM * kSwizzleRow));
+                        const uint64_t db = umma_desc(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow));
 #pragma unroll
-                    for (int k = 0; k < 4; k++)  // +32 bytes (2 x 16 B units) per K step inside the swizzle row
-                        umma_bf16(tmem_d + st * BN, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
-                }
+                        for (int k = 0; k < 4; k++)  // +32 bytes (2 x 16 B units) per K step inside the swizzle row
+                            umma_bf16(tmem_d + (st * MB + m) * BN, da + 2 * k, db + 2 * k, idesc, (c | k) ? 1u : 0u);
+                    }
                 umma_commit(bar_mma(st));  // arrives when the MMAs above have completed (implies before_thread_sync)
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: 8 warps
-        const int quarter = warp & 3;    // TMEM lane quarter this warp may read (warp id % 4)
-        const int chalf = warp >> 2;     // which half of the tile's columns this warp scans
+        // ------------------------------------------------------------------ epilogue: 8 warps per row block
+        const int mblk = warp / kEpiWarps;       // the row block (accumulator) of this warp
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
+        const int chalf = (warp >> 2) & 1;       // which half of the tile's columns this warp scans
         float mx[8], sc[8];
         int imx[8], isc[8];
 #pragma unroll
@@ -288,7 +351,7 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 #pragma unroll 1
             for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
                 uint32_t r[32];
-                tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + st * BN + cb, r);
+                tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (st * MB + mblk) * BN + cb, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (cb + 32 >= (chalf + 1) * (BN / 2)) {
                     // last read of this accumulator by this warp: hand it back before the arithmetic
@@ -326,16 +389,17 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         // (a named barrier over the 8 epilogue warps), the lower half's warps merge -- strict >, so equal scores keep
         // the lower index, which is theirs -- and write ONE entry per (split, row, group).
         const int row = quarter * 32 + lane;
+        float4* xc = xchg + mblk * (kBM * 8);
         if (chalf == 1) {
 #pragma unroll
-            for (int g = 0; g < 8; g++) xchg[row * 8 + g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
+            for (int g = 0; g < 8; g++) xc[row * 8 + g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-        if (chalf == 0) {
-            Top2* dst = part + ((size_t)split * n1pad + (size_t)rb * kBM + row) * 8;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + mblk), "n"(kEpiWarps * 32) : "memory");
+        if (chalf == 0 && (rb0 + mblk) * kBM < n1pad) {  // (a CTA's last row block may lie past the rows)
+            Top2* dst = part + ((size_t)split * n1pad + (size_t)(rb0 + mblk) * kBM + row) * 8;
 #pragma unroll
             for (int g = 0; g < 8; g++) {
-                const float4 o = xchg[row * 8 + g];
+                const float4 o = xc[row * 8 + g];
                 const float ov[2] = {o.x, o.y};
                 const int oi[2] = {__float_as_int(o.z), __float_as_int(o.w)};
 #pragma unroll
@@ -374,11 +438,22 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ a, const fl
 template <int NF>
 __global__ void __launch_bounds__(128)
 match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, const sb_point* __restrict__ pts2,
-            const float* __restrict__ f2, const Top2* __restrict__ part, int nsplit, int n1pad) {
-    const int lane = threadIdx.x & 31;
-    const int p1 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+            const float* __restrict__ f2, const Top2* __restrict__ part, int nsplit, int n1pad, const __grid_constant__ MatchBatch mb) {
+    // TWO rows per warp, one per half-warp (the 16 group candidates of a row are one lane each)
+    const int lane = threadIdx.x & 31, hbase = lane & 16;
+    const int p1 = 2 * (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) + (lane >> 4);
     asm volatile("griddepcontrol.wait;" ::: "memory");  // launched early (programmatic dependent launch): match_mma's partials
-    if (p1 >= n1) return;
+    if (mb.counts) {
+        const int z = blockIdx.y;
+        const int2 pr = batch_pair(mb, z);
+        n1 = min(mb.counts[pr.x], mb.bound);
+        pts1 = mb.pts + (size_t)pr.x * mb.pts_stride; pts2 = mb.pts + (size_t)pr.y * mb.pts_stride;
+        f1 = mb.desc + (size_t)pr.x * mb.desc_stride; f2 = mb.desc + (size_t)pr.y * mb.desc_stride;
+        nsplit = mb.nsplit; n1pad = mb.rows_cap;
+        part += (size_t)z * mb.nsplit * mb.rows_cap * 8;
+    }
+    if ((p1 & ~1) >= n1) return;  // both rows of the warp
+    const bool valid = p1 < n1;
     const int g = (lane >> 1) & 7, k = lane & 1;
     // tensor-core top-2 of the group across the splits. The splits cover increasing column ranges and are taken in
     // order, so strict > keeps the lower index on equal scores, as a running scan would.
@@ -410,8 +485,23 @@ match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, c
     int lo = i1, hi = i2;
     if (lo < 0 || (hi >= 0 && hi < lo)) { const int t = lo; lo = hi; hi = t; }
     const int mine = k == 0 ? lo : hi;
-    float e = 0.f;
-    if (lane < 16 && mine >= 0) e = exact_dot<NF>(f1 + (size_t)p1 * NF, f2 + (size_t)mine * NF);
+    // Only candidates that can reach the result are re-scored exactly. The merge below returns m = the largest group
+    // maximum and s2 = the larger of group 0's second and the second largest group maximum, whatever the order of the
+    // groups; a candidate whose tensor-core score lies more than kMargin (30 x the 3e-5 ranking resolution) below the
+    // second largest group maximum can be neither, so it enters the merge with its approximate score. That leaves 2-3
+    // of the 16 candidates of a row: 16 exact re-scores per row were 4 KB of descriptor reads from L2 per row, which
+    // bound this kernel in the batched form (ncu: 197 us for 32 pairs of 4.9 k rows).
+    constexpr float kMargin = 1e-3f;
+    float t1 = v1, t2 = -1.f;  // top-2 of the groups' (approximate) maxima over the 8 groups of this half-warp
+#pragma unroll
+    for (int o = 2; o < 16; o <<= 1) {
+        const float a = __shfl_xor_sync(0xffffffffu, t1, o), b = __shfl_xor_sync(0xffffffffu, t2, o);
+        t2 = fmaxf(fminf(t1, a), fmaxf(t2, b));
+        t1 = fmaxf(t1, a);
+    }
+    const float approx = mine == i1 ? v1 : v2;
+    float e = approx;
+    if (valid && mine >= 0 && approx >= t2 - kMargin) e = exact_dot<NF>(f1 + (size_t)p1 * NF, f2 + (size_t)mine * NF);
     // the reference's running update (surfd.cu:2610-2625) over (first, second) in index order
     const float e0 = __shfl_sync(0xffffffffu, e, lane & ~1), e1 = __shfl_sync(0xffffffffu, e, lane | 1);
     const int c0 = __shfl_sync(0xffffffffu, mine, lane & ~1), c1 = __shfl_sync(0xffffffffu, mine, lane | 1);
@@ -423,18 +513,18 @@ match_final(sb_point* __restrict__ pts1, int n1, const float* __restrict__ f1, c
         else if (e1 > gs) gs = e1;
     }
     // merge (surfd.cu:2646-2664): start from group 0, the other groups contribute their maxima only
-    float m = __shfl_sync(0xffffffffu, gm, 0), s2 = __shfl_sync(0xffffffffu, gs, 0);
-    int idx = __shfl_sync(0xffffffffu, gi, 0);
+    float m = __shfl_sync(0xffffffffu, gm, hbase), s2 = __shfl_sync(0xffffffffu, gs, hbase);
+    int idx = __shfl_sync(0xffffffffu, gi, hbase);
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-        const float qm = __shfl_sync(0xffffffffu, gm, 2 * q);
-        const int qi = __shfl_sync(0xffffffffu, gi, 2 * q);
+        const float qm = __shfl_sync(0xffffffffu, gm, hbase + 2 * q);
+        const int qi = __shfl_sync(0xffffffffu, gi, hbase + 2 * q);
         if (idx != qi) {
             if (qm > m) { s2 = fmaxf(m, s2); m = qm; idx = qi; }
             else if (qm > s2) s2 = qm;
         }
     }
-    if (lane == 0) {
+    if (valid && (lane & 15) == 0) {
         sb_point* p = pts1 + p1;
         p->score = m;
         p->match = idx;
@@ -517,14 +607,14 @@ EncodeTiledFn encode_tiled() {
 }
 
 // [rows][ktot] bf16 row-major; box = 64 elements (128 B) x box_rows, 128-byte swizzle
-bool make_map(CUtensorMap* m, const void* base, int rows, int ktot, int box_rows) {
+bool make_map(CUtensorMap* m, const void* base, int rows, int ktot, int box_rows, int npairs = 1) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    const cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)rows, (cuuint64_t)npairs};
+    const cuuint64_t strides[2] = {(cuuint64_t)ktot * 2, (cuuint64_t)ktot * 2 * (cuuint64_t)rows};
+    const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -532,7 +622,7 @@ bool make_map(CUtensorMap* m, const void* base, int rows, int ktot, int box_rows
 template <int NF>
 cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_point* d_pts2, int n2, const float* d_f2,
                       MatchScratch& ws, int sm_count, cudaStream_t st) {
-    using Cfg = MatchCfg<NF>;
+    using Cfg = MatchCfg<NF, 1>;
     const int ncand = n2 - (n2 & 31);
     const int n1pad = (n1 + kBM - 1) / kBM * kBM;
     const int ntiles = (ncand + Cfg::BN - 1) / Cfg::BN;
@@ -557,24 +647,25 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     if ((e = grow(ws.b, ws.cap_b, needB)) != cudaSuccess) return e;
     if ((e = grow(ws.part, ws.cap_part, needP)) != cudaSuccess) return e;
 
-    match_prep<NF><<<((n1pad + n2pad) * (NF / 8) + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a, d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b);
+    const MatchBatch none;
+    match_prep<NF><<<((n1pad + n2pad) * (NF / 8) + 255) / 256, 256, 0, st>>>(d_f1, n1, n1pad, (__nv_bfloat16*)ws.a, d_f2, ncand, n2pad, (__nv_bfloat16*)ws.b, none);
     static_assert(sizeof(CUtensorMap) == sizeof(ws.map_a), "tensor map size");
     CUtensorMap& mapA = *reinterpret_cast<CUtensorMap*>(ws.map_a);
     CUtensorMap& mapB = *reinterpret_cast<CUtensorMap*>(ws.map_b);
-    if (ws.map_nf != NF || ws.map_a_base != ws.a || ws.map_a_rows != n1pad) {
+    if (ws.map_nf != NF || ws.map_pairs != 1 || ws.map_a_base != ws.a || ws.map_a_rows != n1pad) {
         if (!make_map(&mapA, ws.a, n1pad, Cfg::KTOT, kBM)) return cudaErrorNotSupported;
         ws.map_a_base = ws.a; ws.map_a_rows = n1pad;
     }
-    if (ws.map_nf != NF || ws.map_b_base != ws.b || ws.map_b_rows != n2pad) {
+    if (ws.map_nf != NF || ws.map_pairs != 1 || ws.map_b_base != ws.b || ws.map_b_rows != n2pad) {
         if (!make_map(&mapB, ws.b, n2pad, Cfg::KTOT, Cfg::BN)) return cudaErrorNotSupported;
         ws.map_b_base = ws.b; ws.map_b_rows = n2pad;
     }
-    ws.map_nf = NF;
+    ws.map_nf = NF; ws.map_pairs = 1;
     // per device (a process may hold contexts on several GPUs), so set on every launch
     static const int use_pdl = getenv("SB_MATCH_PDL") ? atoi(getenv("SB_MATCH_PDL")) : 2;  // 0 off, 1 both, 2 mma only
     static const bool use_keys = !getenv("SB_MATCH_KEYS") || atoi(getenv("SB_MATCH_KEYS")) != 0;
-    if ((e = cudaFuncSetAttribute(match_mma<NF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(match_mma<NF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(match_mma<NF, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(match_mma<NF, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
     // match_mma is a programmatic dependent of match_prep: its CTAs are placed and run their prologue (barrier set-up,
     // tensor-memory allocation) while match_prep is still running, and the producer thread waits at griddepcontrol.wait
     // before the first TMA touches match_prep's output. match_final is launched normally: as a programmatic dependent its
@@ -587,12 +678,54 @@ cudaError_t run_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_poin
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(rbs, nsplit); cfg.blockDim = dim3((kEpiWarps + 1) * 32); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
     cfg.attrs = pdl; cfg.numAttrs = use_pdl ? 1 : 0;
-    if (use_keys) e = cudaLaunchKernelEx(&cfg, match_mma<NF, true>, mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
-    else e = cudaLaunchKernelEx(&cfg, match_mma<NF, false>, mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part);
+    if (use_keys) e = cudaLaunchKernelEx(&cfg, match_mma<NF, true, 1>, mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part, none);
+    else e = cudaLaunchKernelEx(&cfg, match_mma<NF, false, 1>, mapA, mapB, ntiles, tiles_per_split, n1pad, (Top2*)ws.part, none);
     if (e != cudaSuccess) return e;
-    cfg.gridDim = dim3((n1 + 3) / 4); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0;
+    cfg.gridDim = dim3((n1 + 7) / 8); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0;
     cfg.numAttrs = use_pdl == 1 ? 1 : 0;
-    if ((e = cudaLaunchKernelEx(&cfg, match_final<NF>, d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit, n1pad)) != cudaSuccess) return e;
+    if ((e = cudaLaunchKernelEx(&cfg, match_final<NF>, d_pts1, n1, d_f1, d_pts2, d_f2, (const Top2*)ws.part, nsplit, n1pad, none)) != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+// All pairs of a detect batch in one launch sequence; counts stay on the device. Scratch: rows_cap rows per pair.
+template <int NF>
+cudaError_t run_match_batch(sb_point* d_pts, long long pts_stride, const int* d_counts, const float* d_desc, long long desc_stride,
+                            int npairs, const int2* d_pairs, int bound, MatchScratch& ws, int sm_count, cudaStream_t st) {
+    constexpr int MB = NF == 64 ? 2 : 1;  // two row blocks per CTA where the shared memory allows
+    using Cfg = MatchCfg<NF, MB>;
+    MatchBatch mb;
+    mb.counts = d_counts; mb.pairs = d_pairs; mb.pts = d_pts; mb.desc = d_desc; mb.pts_stride = pts_stride; mb.desc_stride = desc_stride;
+    mb.bound = bound;
+    mb.rows_cap = (bound + kBM - 1) / kBM * kBM;   // a multiple of 128, hence of BN
+    const int rbs_cap = (mb.rows_cap / kBM + MB - 1) / MB;  // CTAs along the rows
+    // enough CTAs for about two waves; with many pairs every CTA keeps its A' rows for ALL column tiles (no split)
+    mb.nsplit = std::max(1, std::min(8, (2 * sm_count + npairs * rbs_cap - 1) / (npairs * rbs_cap)));
+    const size_t needO = (size_t)npairs * mb.rows_cap * Cfg::KTOT * 2;
+    const size_t needP = (size_t)npairs * mb.nsplit * mb.rows_cap * 8 * sizeof(Top2);
+    cudaError_t e;
+    auto grow = [&](void*& p, size_t& cap, size_t need) -> cudaError_t {
+        if (cap >= need) return cudaSuccess;
+        if (p) { cudaError_t r = cudaFree(p); if (r != cudaSuccess) return r; p = nullptr; cap = 0; }
+        cudaError_t r = cudaMalloc(&p, need);
+        if (r == cudaSuccess) cap = need;
+        return r;
+    };
+    if ((e = grow(ws.a, ws.cap_a, needO)) != cudaSuccess) return e;
+    if ((e = grow(ws.b, ws.cap_b, needO)) != cudaSuccess) return e;
+    if ((e = grow(ws.part, ws.cap_part, needP)) != cudaSuccess) return e;
+    CUtensorMap& mapA = *reinterpret_cast<CUtensorMap*>(ws.map_a);
+    CUtensorMap& mapB = *reinterpret_cast<CUtensorMap*>(ws.map_b);
+    if (ws.map_nf != NF || ws.map_pairs != npairs || ws.map_a_base != ws.a || ws.map_a_rows != mb.rows_cap ||
+        ws.map_b_base != ws.b || ws.map_b_rows != mb.rows_cap) {
+        if (!make_map(&mapA, ws.a, mb.rows_cap, Cfg::KTOT, kBM, npairs) || !make_map(&mapB, ws.b, mb.rows_cap, Cfg::KTOT, Cfg::BN, npairs))
+            return cudaErrorNotSupported;
+        ws.map_a_base = ws.a; ws.map_b_base = ws.b; ws.map_a_rows = ws.map_b_rows = mb.rows_cap; ws.map_nf = NF; ws.map_pairs = npairs;
+    }
+    match_prep<NF><<<dim3((mb.rows_cap * (NF / 8) + 255) / 256, 2 * npairs), 256, 0, st>>>(nullptr, 0, 0, (__nv_bfloat16*)ws.a, nullptr, 0, 0,
+                                                                                          (__nv_bfloat16*)ws.b, mb);
+    if ((e = cudaFuncSetAttribute(match_mma<NF, true, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)) != cudaSuccess) return e;
+    match_mma<NF, true, MB><<<dim3(rbs_cap, mb.nsplit, npairs), Cfg::THREADS, Cfg::SMEM, st>>>(mapA, mapB, 0, 0, 0, (Top2*)ws.part, mb);
+    match_final<NF><<<dim3(mb.rows_cap / 8, npairs), 128, 0, st>>>(nullptr, 0, nullptr, nullptr, nullptr, (const Top2*)ws.part, 0, 0, mb);
     return cudaGetLastError();
 }
 
@@ -606,6 +739,15 @@ cudaError_t launch_match(sb_point* d_pts1, int n1, const float* d_f1, const sb_p
     if (nfeatures < 1 || nfeatures > 256) return cudaErrorInvalidValue;
     match_generic_kernel<<<(n1 + 3) / 4, 128, 4 * nfeatures * sizeof(float), st>>>(d_pts1, n1, d_f1, d_pts2, n2 - (n2 & 31), d_f2, nfeatures);
     return cudaGetLastError();
+}
+
+cudaError_t launch_match_batch(sb_point* d_pts, long long pts_stride, const int* d_counts, const float* d_desc, long long desc_stride,
+                               int npairs, const int* d_pairs, int bound, int nfeatures, MatchScratch& ws, int sm_count, cudaStream_t st) {
+    if (npairs <= 0 || bound <= 0) return cudaSuccess;
+    const int2* pr = reinterpret_cast<const int2*>(d_pairs);
+    if (nfeatures == 64) return run_match_batch<64>(d_pts, pts_stride, d_counts, d_desc, desc_stride, npairs, pr, bound, ws, sm_count, st);
+    if (nfeatures == 128) return run_match_batch<128>(d_pts, pts_stride, d_counts, d_desc, desc_stride, npairs, pr, bound, ws, sm_count, st);
+    return cudaErrorInvalidValue;  // other descriptor sizes: the single-pair call (match_generic_kernel)
 }
 
 void free_match_scratch(MatchScratch& ws) {

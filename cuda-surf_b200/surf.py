@@ -129,6 +129,16 @@ class Surfor:
                                     data2.d_data.data_ptr(), data2.num_pts, features2.data_ptr(), C.c_void_p(st))
         B.check(rc, self._ctx)
 
+    def match_pairs_async(self, points, counts, desc, npairs, bound, pairs=None, stream=None):
+        """Surfor::match for all stereo pairs of a detect batch at once, counts read on the device (sb_match_pairs_async):
+        points uint8 CUDA [n, max_pts*48], counts int32 CUDA [n], desc float32 CUDA [n, max_pts, nf] as written by
+        detect_batch; pair z is frames (2z, 2z+1) unless `pairs` (int32 CUDA [npairs, 2]) says otherwise."""
+        import torch
+        st = (stream or torch.cuda.current_stream(points.device)).cuda_stream
+        rc = B.lib().sb_match_pairs_async(self._ctx, points.data_ptr(), points.stride(0) // 48, counts.data_ptr(), desc.data_ptr(),
+                                          desc.stride(0), npairs, pairs.data_ptr() if pairs is not None else None, bound, C.c_void_p(st))
+        B.check(rc, self._ctx)
+
     def match_filter(self, data1, data2, max_ambiguity=0.8, laplace=False, cross=False):
         """Pairs (idx1, idx2, score, ambiguity) of the rows of data1 accepted by the consumer-side ratio test
         `ambiguity < max_ambiguity` (BASELINE config 5), optionally with equal Laplacian signs and a symmetric

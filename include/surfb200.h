@@ -118,6 +118,19 @@ int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const floa
 int sb_match_async(sb_ctx* ctx, sb_point* d_pts1, int n1, const float* d_feat1, const sb_point* d_pts2, int n2,
                    const float* d_feat2, void* stream);
 
+/* Surfor::match for ALL stereo pairs of a detect batch in one launch sequence (BASELINE config 5: what main.cpp:246-251
+ * does per pair), with the keypoint counts read on the device: nothing travels to the host between
+ * sb_detect_batch_async and the matching.
+ *   d_points [nframes][pts_stride] sb_point, d_counts [nframes], d_desc [nframes][desc_stride floats]: the outputs of
+ *            sb_detect_batch_async (pts_stride = max_pts, desc_stride = max_pts * nfeatures)
+ *   d_pairs  device array of npairs (frame1, frame2) index pairs; NULL: pair z is (2z, 2z + 1)
+ *   bound    upper bound of the keypoint counts that take part (a frame with more is matched on its first `bound`
+ *            points); sizes the scratch: npairs * bound * (6 * nfeatures + 128 * splits) bytes, grown on the first call
+ * Per pair the results are those of sb_match (score, match, match_x, match_y, ambiguity of frame1's points).
+ * 64- and 128-d descriptors only. Enqueued on `stream`, no synchronisation.                                        */
+int sb_match_pairs_async(sb_ctx* ctx, sb_point* d_points, long long pts_stride, const int* d_counts, const float* d_desc,
+                         long long desc_stride, int npairs, const int* d_pairs, int bound, void* stream);
+
 /* Consumer-side acceptance of match results (the reference draws every row's best candidate,
  * main.cpp:59-70, and leaves the ratio test to the consumer of SurfPoint::ambiguity). Rows of set 1 with
  * match >= 0 and ambiguity < max_ambiguity are compacted, in row order, into (idx1, idx2, score, ambiguity).

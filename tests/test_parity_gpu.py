@@ -729,3 +729,57 @@ def test_tma_descriptor_path_equals_gather_path(monkeypatch):
             l2 = np.linalg.norm(f1[k1] - f0[k0], axis=1)
             assert l2.max() <= 1e-5, f"{w}x{h} rep {rep}: L2 max {l2.max():.3e} at row {l2.argmax()}"
         det1.close()
+
+
+def test_match_pairs_equals_match_per_pair():
+    """sb_match_pairs_async (all stereo pairs of a detect batch in one launch sequence, counts read on the device) gives,
+    per pair, exactly the five match fields of sb_match on the same keypoints and descriptors; a custom pair list, a
+    bound below a frame's count (the first `bound` points take part) and an empty frame are covered."""
+    sb = _sb()
+    torch = _torch()
+    w, h, NF, MAXP = 640, 480, 4, 4096
+    det = make_det(w, h, 4, max_pts=MAXP, batch=2 * NF)
+    pitch = sb.iAlignUp(w, 128)
+    buf = np.zeros((2 * NF, h, pitch), np.uint8)
+    for p in range(NF):
+        buf[2 * p, :, :w] = sb.synth_frame(w, h, 5000 + p)
+        buf[2 * p + 1, :, :w] = sb.synth_frame(w, h, 5000 + p, 12, 2, (5000 + p) ^ 0xA5A5)
+    buf[7] = 0  # an empty right frame: pair 3 has no candidates
+    d = torch.from_numpy(buf).cuda()
+    pts = torch.zeros((2 * NF, MAXP * 48), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(2 * NF, dtype=torch.int32, device="cuda")
+    desc = torch.zeros((2 * NF, MAXP, 64), dtype=torch.float32, device="cuda")
+    det.detect_batch(d, pitch, pts, cnt, desc)
+    torch.cuda.synchronize()
+    counts = cnt.cpu().numpy()
+    assert counts[0] > 300 and counts[7] == 0
+
+    class View:
+        def __init__(self, f, n): self.d_data = pts[f]; self.num_pts = int(n); self.h_data = None
+
+    def fields(f, n):
+        a = pts[f].cpu().numpy().view(sb.POINT_DTYPE)[:n]
+        return {k: a[k].copy() for k in ("score", "match", "match_x", "match_y", "ambiguity")}
+
+    def clear():
+        v = pts.view(2 * NF, MAXP, 48)
+        v[:, :, 28:48] = 0  # score, match, match_x, match_y, ambiguity
+        torch.cuda.synchronize()
+
+    for bound, pairs in [(MAXP, None), (256, None), (MAXP, [(0, 1), (2, 0), (1, 3), (5, 4)])]:
+        plist = pairs or [(2 * z, 2 * z + 1) for z in range(NF)]
+        want = []
+        clear()
+        for a, b in plist:
+            det.match_async(View(a, min(counts[a], bound)), View(b, min(counts[b], bound)), desc[a], desc[b])
+            torch.cuda.synchronize()
+            want.append(fields(a, min(counts[a], bound)))
+            clear()
+        dp = torch.tensor(pairs, dtype=torch.int32, device="cuda") if pairs else None
+        det.match_pairs_async(pts, cnt, desc, len(plist), bound, dp)
+        torch.cuda.synchronize()
+        got = [fields(a, min(counts[a], bound)) for a, _ in plist]
+        for z, (g, wnt) in enumerate(zip(got, want)):
+            for k in g:
+                assert np.array_equal(g[k], wnt[k]), f"bound {bound} pairs {pairs} pair {z} field {k}"
+    det.close()
