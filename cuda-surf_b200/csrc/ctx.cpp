@@ -332,7 +332,7 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
     }
     info->resp_floats = t;
     // (the octave-0 shared-memory Hessian kernel exists for the reference's default geometry only, hessian.cu)
-    const bool fast0 = P.sampling == 2 && P.init_lobe == 3 && P.max_scale == 5;
+    const bool fast0 = (P.sampling == 2 || P.sampling == 4) && P.init_lobe == 3 && P.max_scale == 5;
     const int nhess = fast0 ? (P.noctaves > 1 ? 2 : 1) : 1;
     info->cand_capacity = ctx->cand_cap;
     info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + nhess + 2 /*nms scan, refine*/ + 1 /*clamp*/ + (P.upright ? 1 : 2) +

@@ -148,25 +148,37 @@ hessian_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Iphase, 
 // Only for the reference's default geometry (sampling 2, lobes 3,5,7,9,11); anything else takes the
 // generic kernel.
 constexpr int kTW = 32, kTH = 16;            // outputs per tile
-constexpr int kPW = 96, kPH = 64;            // staged patch (integral elements)
-constexpr int kQW = kPW / 2, kQH = kPH / 2;  // plane dims
-constexpr int kPlane = kQW * kQH;            // 1536 words
-constexpr int kHalo = 16;                    // patch origin = 2*tile origin - kHalo
-// the two planes of odd patch rows start 16 words later: a staging warp covers the end of one patch row and the start of
-// the next (24 int4 per row), whose 64-bit stores otherwise meet in banks 0..15 (ncu: 7 % of the wavefronts were conflicts)
-constexpr int kRowPar = 2 * kPlane + 16;
+constexpr int kHalo = 16;                    // patch origin = D * tile origin - kHalo (the widest corner offset is 17, the last sample D px short of the tile's end)
+// D = sampling step of octave 0 in pixels: 2 (the reference's default) or 4 (doubled=true, where the 2x frame is sampled every
+// 4th pixel). The staged patch is D*32+32 x D*16+32 integral elements, de-interleaved into D x D (row phase, column
+// phase) planes, so the 32 lanes of a warp -- D pixels apart -- read 32 consecutive words for every corner.
+template <int D> struct O0 {
+    static constexpr int PW = D * kTW + 2 * kHalo, PH = D * kTH + 2 * kHalo;  // 96 x 64 (D = 2), 160 x 96 (D = 4)
+    static constexpr int QW = PW / D, QH = PH / D;                              // plane dims
+    static constexpr int Plane = QW * QH;
+    // D = 2: the two planes of odd patch rows start 16 words later: a staging warp covers the end of one patch row and the
+    // start of the next (24 int4 per row), whose 64-bit stores otherwise meet in banks 0..15 (ncu: 7 % of the wavefronts
+    // were conflicts)
+    static constexpr int RowPhase = D * Plane + (D == 2 ? 16 : 0);
+    static constexpr int Words = D * RowPhase;
+    static constexpr int Int4PerRow = PW / 4;
+    static constexpr int Int4 = PH * Int4PerRow;  // 1536 (D = 2), 3840 (D = 4)
+    static_assert(Int4 % 256 == 0, "staging assumes a whole number of int4 per thread");
+};
 
-// word offset of patch element (cy + dy, cx + dx) relative to the thread base (ly*kQW + lx)
+// word offset of patch element (cy + dy, cx + dx) relative to the thread base (ly*QW + lx)
+template <int D>
 __host__ __device__ constexpr int corner_off(int dx, int dy) {
-    return ((dy + kHalo) & 1) * kRowPar + ((dx + kHalo) & 1) * kPlane + ((dy + kHalo) >> 1) * kQW + ((dx + kHalo) >> 1);
+    return ((dy + kHalo) & (D - 1)) * O0<D>::RowPhase + ((dx + kHalo) & (D - 1)) * O0<D>::Plane + ((dy + kHalo) / D) * O0<D>::QW +
+           ((dx + kHalo) / D);
 }
 
 // ctr = the four corners (0,0), (1,0), (0,1), (1,1) [as (dx,dy)] around the sample: every layer's Dxy uses them, so
 // they are read once per sample instead of once per layer (16 of the 160 shared-memory words of a sample)
-template <int L>
+template <int L, int D>
 __device__ __forceinline__ float response_smem(const int* __restrict__ b, float norm, const int (&ctr)[4]) {
     constexpr int x2 = L / 2, x3 = 2 * x2, x4 = 3 * x2;
-#define C_(dx, dy) b[corner_off(dx, dy)]
+#define C_(dx, dy) b[corner_off<D>(dx, dy)]
     // same corners as hessian_response(): rows/cols are those of getSum (surfd.cu:334-343)
     const int wide = C_(L + x2 + 1, x3 + 1) + C_(-L - x2, -x3) - C_(L + x2 + 1, -x3) - C_(-L - x2, x3 + 1);
     const int midx = C_(x2 + 1, x3 + 1) + C_(-x2, -x3) - C_(x2 + 1, -x3) - C_(-x2, x3 + 1);
@@ -189,13 +201,13 @@ __device__ __forceinline__ float response_smem(const int* __restrict__ b, float 
     return __fmul_rn(det, norm);
 }
 
-template <int L, int LAYER>
+template <int L, int LAYER, int D>
 __device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict__ b, float* __restrict__ Rf, int ix, int iy,
                                            const int (&ctr)[4]) {
     const OctaveP& q = P.oct[0];
     const int bd = q.b1[LAYER];
     if (ix < bd || ix >= q.sw - bd || iy < bd || iy >= q.sh - bd) return;
-    const float v = response_smem<L>(b, q.norm[LAYER], ctr);
+    const float v = response_smem<L, D>(b, q.norm[LAYER], ctr);
     Rf[q.resp_off + (size_t)LAYER * q.osz + (size_t)iy * q.sp + ix] = v;
     // layers 2 and 4 are what halfImage copies into layers 0 and 1 of octave 1 (surf.cpp:250-258)
     if ((LAYER == 2 || LAYER == 4) && P.noctaves > 1 && ((ix | iy) & 1) == 0) {
@@ -205,37 +217,53 @@ __device__ __forceinline__ void layer_smem(const PipeP& P, const int* __restrict
     }
 }
 
-// grid (tiles_x * tiles_y, nframes), 256 threads, 24 KB static shared memory
-__global__ void __launch_bounds__(256, 4)
+// grid (tiles_x * tiles_y, nframes), 256 threads, dynamic shared memory O0<D>::Words ints (24.6 KB for D = 2, 61.4 KB for D = 4)
+template <int D>
+__global__ void __launch_bounds__(256, D == 2 ? 4 : 3)
 hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, float* __restrict__ Rbase, int tiles_x) {
     pdl_wait();
-    __shared__ __align__(16) int patch[4 * kPlane + 16];
+    using G = O0<D>;
+    extern __shared__ __align__(16) int patch[];
     const int f = blockIdx.y;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int* I = Ibase + (size_t)f * P.istride + P.ip;
-    const int X0 = 2 * kTW * tx - kHalo, Y0 = 2 * kTH * ty - kHalo;
-    // stage: 64 rows x 24 int4; (x0,x2) go to the even-column plane, (x1,x3) to the odd one
-    // (1536 int4 = 6 per thread, all six loads in flight before the first store waits on one: as a plain loop every
-    // position was its own memory round trip)
-    static_assert(kPH * (kPW / 4) == 6 * 256, "staging assumes 6 int4 per thread");
-    {
-        int4 v[6];
+    const int X0 = D * kTW * tx - kHalo, Y0 = D * kTH * ty - kHalo;
+    // stage: PH rows x PW/4 int4; element x of a row goes to column-phase plane x mod D
+    // (all loads of a thread are in flight before the first store waits on one: as a plain loop every position was its own
+    // memory round trip)
+    constexpr int PER = G::Int4 / 256;  // 6 (D = 2), 15 (D = 4)
+    constexpr int NB = PER % 6 == 0 ? 6 : 5;  // loads in flight per thread: all 6, or 3 batches of 5
 #pragma unroll
-        for (int it = 0; it < 6; it++) {
-            const int t = threadIdx.x + 256 * it;
-            const int row = t / (kPW / 4), k = t - row * (kPW / 4);
-            const int y = Y0 + row, x = X0 + 4 * k;
-            const bool in = y >= 0 && y < P.ih && x >= 0 && x + 3 < P.ip;
-            const int4 ld = __ldg(reinterpret_cast<const int4*>(I + (in ? (size_t)y * P.ip + x : (size_t)0)));
-            v[it] = in ? ld : make_int4(0, 0, 0, 0);
+    for (int it0 = 0; it0 < PER; it0 += NB) {
+        int4 v[NB];
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int it = it0 + u;
+            if (it < PER) {
+                const int t = threadIdx.x + 256 * it;
+                const int row = t / G::Int4PerRow, k = t - row * G::Int4PerRow;
+                const int y = Y0 + row, x = X0 + 4 * k;
+                const bool in = y >= 0 && y < P.ih && x >= 0 && x + 3 < P.ip;
+                const int4 ld = __ldg(reinterpret_cast<const int4*>(I + (in ? (size_t)y * P.ip + x : (size_t)0)));
+                v[u] = in ? ld : make_int4(0, 0, 0, 0);
+            }
         }
 #pragma unroll
-        for (int it = 0; it < 6; it++) {
-            const int t = threadIdx.x + 256 * it;
-            const int row = t / (kPW / 4), k = t - row * (kPW / 4);
-            int* dst = patch + (row & 1) * kRowPar + (row >> 1) * kQW + 2 * k;
-            *reinterpret_cast<int2*>(dst) = make_int2(v[it].x, v[it].z);
-            *reinterpret_cast<int2*>(dst + kPlane) = make_int2(v[it].y, v[it].w);
+        for (int u = 0; u < NB; u++) {
+            const int it = it0 + u;
+            if (it < PER) {
+                const int t = threadIdx.x + 256 * it;
+                const int row = t / G::Int4PerRow, k = t - row * G::Int4PerRow;
+                int* dst = patch + (row & (D - 1)) * G::RowPhase + (row / D) * G::QW;
+                if (D == 2) {
+                    dst += 2 * k;
+                    *reinterpret_cast<int2*>(dst) = make_int2(v[u].x, v[u].z);
+                    *reinterpret_cast<int2*>(dst + G::Plane) = make_int2(v[u].y, v[u].w);
+                } else {
+                    dst += k;
+                    dst[0] = v[u].x; dst[G::Plane] = v[u].y; dst[2 * G::Plane] = v[u].z; dst[3 * G::Plane] = v[u].w;
+                }
+            }
         }
     }
     __syncthreads();
@@ -246,24 +274,31 @@ hessian_o0_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
     for (int hrow = 0; hrow < 2; hrow++) {
         const int lyy = ly + 8 * hrow;
         const int iy = kTH * ty + lyy;
-        const int* b = patch + lyy * kQW + lx;
-        const int ctr[4] = {b[corner_off(0, 0)], b[corner_off(1, 0)], b[corner_off(0, 1)], b[corner_off(1, 1)]};
-        layer_smem<3, 0>(P, b, Rf, ix, iy, ctr);
-        layer_smem<5, 1>(P, b, Rf, ix, iy, ctr);
-        layer_smem<7, 2>(P, b, Rf, ix, iy, ctr);
-        layer_smem<9, 3>(P, b, Rf, ix, iy, ctr);
-        layer_smem<11, 4>(P, b, Rf, ix, iy, ctr);
+        const int* b = patch + lyy * G::QW + lx;
+        const int ctr[4] = {b[corner_off<D>(0, 0)], b[corner_off<D>(1, 0)], b[corner_off<D>(0, 1)], b[corner_off<D>(1, 1)]};
+        layer_smem<3, 0, D>(P, b, Rf, ix, iy, ctr);
+        layer_smem<5, 1, D>(P, b, Rf, ix, iy, ctr);
+        layer_smem<7, 2, D>(P, b, Rf, ix, iy, ctr);
+        layer_smem<9, 3, D>(P, b, Rf, ix, iy, ctr);
+        layer_smem<11, 4, D>(P, b, Rf, ix, iy, ctr);
     }
 }
 
 cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, const int* d_integral_ph, float* d_resp,
                            cudaStream_t st) {
     const OctaveP& q0 = P.oct[0];
-    const bool fast0 = P.sampling == 2 && P.init_lobe == 3 && P.max_scale == 5 && q0.s0 == 0 && q0.nl == 5;
+    const bool fast0 = (P.sampling == 2 || P.sampling == 4) && P.init_lobe == 3 && P.max_scale == 5 && q0.s0 == 0 && q0.nl == 5;
     int first_tile = 0;
     if (fast0) {
         const int tiles_x = (q0.sw + kTW - 1) / kTW, tiles_y = (q0.sh + kTH - 1) / kTH;
-        const cudaError_t e = launch_dep(hessian_o0_kernel, dim3(tiles_x * tiles_y, nframes), dim3(256), 0, st, P, d_integral, d_resp, tiles_x);
+        cudaError_t e;
+        if (P.sampling == 2) {
+            e = launch_dep(hessian_o0_kernel<2>, dim3(tiles_x * tiles_y, nframes), dim3(256), O0<2>::Words * sizeof(int), st, P, d_integral, d_resp, tiles_x);
+        } else {
+            e = cudaFuncSetAttribute(hessian_o0_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(O0<4>::Words * sizeof(int)));
+            if (e == cudaSuccess)
+                e = launch_dep(hessian_o0_kernel<4>, dim3(tiles_x * tiles_y, nframes), dim3(256), O0<4>::Words * sizeof(int), st, P, d_integral, d_resp, tiles_x);
+        }
         if (e != cudaSuccess) return e;
         first_tile = P.noctaves > 1 ? P.oct[1].hess_tile0 : P.hess_tiles;
     }

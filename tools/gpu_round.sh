@@ -15,7 +15,7 @@ if [ $rc -eq 0 ]; then
       python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${T}_ncu_bench.log 2>&1; echo "ncu rc=$?"
   echo "== ncu full"
   timeout 300 python tools/prof_kernels.py 8 1 > gpurun_out/${T}_prof_plain.log 2>&1 && \
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'hessian|describe|nms_|integral' -s 14 -c 7 -f -o gpurun_out/${T}_full python tools/prof_kernels.py 8 1 > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"; cat gpurun_out/${T}_prof_plain.log; tail -3 gpurun_out/${T}_ncu_full.log
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"hessian|describe|nms_|integral" -s 14 -c 7 -f -o gpurun_out/${T}_full python tools/prof_kernels.py 8 1 > gpurun_out/${T}_ncu_full.log 2>&1; echo "ncu full rc=$?"; cat gpurun_out/${T}_prof_plain.log; tail -3 gpurun_out/${T}_ncu_full.log
   echo "== ncu dram traffic of the dominant kernel at the bench batch (64 frames)"
   timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"describe_upright|hessian|nms_scan|integral" -s 12 -c 6 --csv --log-file gpurun_out/${T}_traffic.csv python tools/prof_kernels.py 64 1 > /dev/null 2>&1; echo "traffic rc=$?"; tail -3 gpurun_out/${T}_traffic.csv
 fi

@@ -18,5 +18,5 @@ for w, h, seed in cases:
             det.detectAndCompute(d, data, (w, h, pitch), desc_out=dd)
             ts.append((time.perf_counter() - a) * 1e3)
         ts = ts[20:]
-        print(f"{w}x{h} upright={upright} PDL={os.environ.get('SURFB200_PDL','1')}: p50 {np.percentile(ts,50):.4f} ms p90 {np.percentile(ts,90):.4f} ms, {data.num_pts} keypoints")
+        print(f"{w}x{h} upright={upright} PDL={os.environ.get('SURFB200_PDL','0')}: p50 {np.percentile(ts,50):.4f} ms p90 {np.percentile(ts,90):.4f} ms, {data.num_pts} keypoints")
         det.close()
