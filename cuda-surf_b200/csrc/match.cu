@@ -56,7 +56,7 @@ template <int NF, int MB = 1> struct MatchCfg {
     static_assert(MB * XCHG_BYTES <= kStages * B_BYTES, "exchange buffers alias the B' stages");
     static constexpr int SMEM = MB * A_BYTES + kStages * B_BYTES + 1024 /*alignment slack*/ + 128 /*barriers*/;
     static constexpr int TMEM_COLS = kStages * MB * BN;     // a power of two >= 32, <= 512
-    static constexpr int THREADS = (kEpiWarps * MB + 1) * 32;
+    static constexpr int THREADS = (kEpiWarps + 1) * 32;  // 8 epilogue warps (each scans its rows of all MB accumulators) + the producer
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -211,7 +211,7 @@ struct __align__(16) Top2 { float mx, sc; int imx, isc; };  // 16 bytes, moved a
 // ready, operands consumed), `free` (the eight epilogue warps have read the accumulator). Round-1 v1 did load -> MMA ->
 // epilogue strictly one after the other (ncu: tensor pipe active 12.5 % of the kernel).
 template <int NF, bool KEYS, int MB>
-__global__ void __launch_bounds__((kEpiWarps * MB + 1) * 32, 1)
+__global__ void __launch_bounds__((kEpiWarps + 1) * 32, 1)
 match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles, int tiles_per_split,
           int n1pad, Top2* __restrict__ part, const __grid_constant__ MatchBatch mb) {
     using Cfg = MatchCfg<NF, MB>;
@@ -256,10 +256,10 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         for (int c = 0; c < KCH; c++)
             tma_load_3d(smem_u32(sB + st * Cfg::B_BYTES + c * BN * kSwizzleRow), &mapB, bar_full(st), c * 64, (t0 + i) * BN, zpair);
     };
-    if (tid == kEpiWarps * MB * 32) {
+    if (tid == kEpiWarps * 32) {
         // the producer thread arms the barriers itself and starts the first loads at once: they fly while warp 1 allocates
         // tensor memory and the CTA meets at the barrier below
-        for (int st = 0; st < kStages; st++) { mbar_init(bar_full(st), 1); mbar_init(bar_mma(st), 1); mbar_init(bar_free(st), kEpiWarps * MB); }
+        for (int st = 0; st < kStages; st++) { mbar_init(bar_full(st), 1); mbar_init(bar_mma(st), 1); mbar_init(bar_free(st), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // (programmatic dependent launch: everything above overlaps match_prep; its output is first touched here)
@@ -275,7 +275,7 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == kEpiWarps * MB) {
+    if (warp == kEpiWarps) {
         // ------------------------------------------------------------------ producer: one thread
         if (lane == 0 && n > 0) {
             for (int i = 0; i < n; i++) {
@@ -301,14 +301,16 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue: 8 warps per row block
-        const int mblk = warp / kEpiWarps;       // the row block (accumulator) of this warp
+        // ------------------------------------------------------------------ epilogue: 8 warps
         const int quarter = warp & 3;            // TMEM lane quarter this warp may read (warp id % 4)
         const int chalf = (warp >> 2) & 1;       // which half of the tile's columns this warp scans
-        float mx[8], sc[8];
-        int imx[8], isc[8];
+        // per row block m of the CTA: the thread's row is TMEM lane quarter*32 + lane of accumulator (stage, m)
+        float mx[MB][8], sc[MB][8];
+        int imx[MB][8], isc[MB][8];
 #pragma unroll
-        for (int g = 0; g < 8; g++) { mx[g] = 0.f; sc[g] = 0.f; imx[g] = -1; isc[g] = -1; }
+        for (int m = 0; m < MB; m++)
+#pragma unroll
+            for (int g = 0; g < 8; g++) { mx[m][g] = 0.f; sc[m][g] = 0.f; imx[m][g] = -1; isc[m][g] = -1; }
         // Inside a round of up to kRound tiles the running top-2 of a group is kept on PACKED KEYS: the score's bit pattern
         // with its low 6 mantissa bits replaced by 63 - (candidate number inside the round). Positive floats order like
         // signed integers, so a score costs one LOP3 and three integer min/max instead of two compares, three selects
@@ -317,69 +319,79 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         // a matter of WHICH two candidates match_final re-scores exactly; equal truncated scores prefer the lower index,
         // as the reference's strict > does. Key 0 = (score 0, candidate 63) is the empty slot.
         constexpr int kRound = 63 / (BN / 16);  // BN/16 candidates of one group per tile and thread (BN/2 columns / 8 groups); code 63 = empty
-        int k1[8], k2[8];
+        int k1[MB][8], k2[MB][8];
         auto fold = [&](int round0) {  // keys of the round starting at tile round0 -> (value, index), merged into the running top-2
 #pragma unroll
-            for (int g = 0; g < 8; g++) {
+            for (int m = 0; m < MB; m++)
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int key = q == 0 ? k1[g] : k2[g];
-                    const int code = 63 - (key & 63);
-                    if (code != 63) {
-                        // code = tile-in-round * (BN/16) + chunk * 4 + column-in-group
-                        const int per_tile = BN / 16;
-                        const int ti = code / per_tile, rest = code - ti * per_tile;
-                        const int col = (t0 + round0 + ti) * BN + chalf * (BN / 2) + (rest >> 2) * 32 + g * 4 + (rest & 3);
-                        const float s = __int_as_float(key & ~63);
-                        if (s > mx[g]) { sc[g] = mx[g]; isc[g] = imx[g]; mx[g] = s; imx[g] = col; }
-                        else if (s > sc[g]) { sc[g] = s; isc[g] = col; }
+                for (int g = 0; g < 8; g++) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int key = q == 0 ? k1[m][g] : k2[m][g];
+                        const int code = 63 - (key & 63);
+                        if (code != 63) {
+                            // code = tile-in-round * (BN/16) + chunk * 4 + column-in-group
+                            const int per_tile = BN / 16;
+                            const int ti = code / per_tile, rest = code - ti * per_tile;
+                            const int col = (t0 + round0 + ti) * BN + chalf * (BN / 2) + (rest >> 2) * 32 + g * 4 + (rest & 3);
+                            const float s = __int_as_float(key & ~63);
+                            if (s > mx[m][g]) { sc[m][g] = mx[m][g]; isc[m][g] = imx[m][g]; mx[m][g] = s; imx[m][g] = col; }
+                            else if (s > sc[m][g]) { sc[m][g] = s; isc[m][g] = col; }
+                        }
                     }
+                    k1[m][g] = 0; k2[m][g] = 0;
                 }
-                k1[g] = 0; k2[g] = 0;
-            }
         };
 #pragma unroll
-        for (int g = 0; g < 8; g++) { k1[g] = 0; k2[g] = 0; }
+        for (int m = 0; m < MB; m++)
+#pragma unroll
+            for (int g = 0; g < 8; g++) { k1[m][g] = 0; k2[m][g] = 0; }
         int round0 = 0;
         for (int i = 0; i < n; i++) {
             const int st = i % kStages, use = i / kStages;
             if (KEYS && i - round0 == kRound) { fold(round0); round0 = i; }
             mbar_wait(bar_mma(st), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // thread == (row = TMEM lane, half of the columns); 32 accumulator columns per tcgen05.ld; the 8 groups of a
-            // 32-column chunk are independent dependency chains (ILP 8).
-#pragma unroll 1
-            for (int cb = chalf * (BN / 2); cb < (chalf + 1) * (BN / 2); cb += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (st * MB + mblk) * BN + cb, r);
+            // thread == (row = TMEM lane, half of the columns). All of this warp's columns of one accumulator are read
+            // first (one wait), then scanned; after the read of the LAST accumulator of the stage it goes back to the MMA
+            // issuer. The 8 groups of a 32-column chunk are independent dependency chains (ILP 8).
+            constexpr int NCH = BN / 2 / 32;  // 32-column chunks per warp and accumulator: 2 (BN = 128) or 1 (BN = 64)
+#pragma unroll
+            for (int m = 0; m < MB; m++) {
+                uint32_t r[NCH][32];
+#pragma unroll
+                for (int c = 0; c < NCH; c++)
+                    tmem_ld32(tmem_d + ((uint32_t)(quarter * 32) << 16) + (st * MB + m) * BN + chalf * (BN / 2) + 32 * c, r[c]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (cb + 32 >= (chalf + 1) * (BN / 2)) {
-                    // last read of this accumulator by this warp: hand it back before the arithmetic
+                if (m == MB - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_free(st)) : "memory");
                 }
-                // 63 - candidate number of column-in-group 0 of this chunk; the three others follow downwards
-                const int code0 = 63 - ((i - round0) * (BN / 16) + ((cb - chalf * (BN / 2)) >> 5) * 4);
-                if (KEYS) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int g = j >> 2;
-                        const int key = (int)(r[j] & 0xFFFFFFC0u) | (code0 - (j & 3));
-                        const int t = min(k1[g], key);
-                        k1[g] = max(k1[g], key);
-                        k2[g] = max(k2[g], t);
-                    }
-                } else {
-                    const int col0 = (t0 + i) * BN + cb;  // multiple of 32: group of column j is (j % 32) / 4
+                for (int c = 0; c < NCH; c++) {
+                    // 63 - candidate number of column-in-group 0 of this chunk; the three others follow downwards
+                    const int code0 = 63 - ((i - round0) * (BN / 16) + c * 4);
+                    if (KEYS) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int g = j >> 2;
-                        const float s = __uint_as_float(r[j]);
-                        const bool gt1 = s > mx[g], gt2 = s > sc[g];
-                        isc[g] = gt1 ? imx[g] : (gt2 ? col0 + j : isc[g]);
-                        imx[g] = gt1 ? col0 + j : imx[g];
-                        sc[g] = fmaxf(sc[g], fminf(mx[g], s));
-                        mx[g] = fmaxf(mx[g], s);
+                        for (int j = 0; j < 32; j++) {
+                            const int g = j >> 2;
+                            const int key = (int)(r[c][j] & 0xFFFFFFC0u) | (code0 - (j & 3));
+                            const int t = min(k1[m][g], key);
+                            k1[m][g] = max(k1[m][g], key);
+                            k2[m][g] = max(k2[m][g], t);
+                        }
+                    } else {
+                        const int col0 = (t0 + i) * BN + chalf * (BN / 2) + 32 * c;  // multiple of 32: group of column j is (j % 32) / 4
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const int g = j >> 2;
+                            const float s = __uint_as_float(r[c][j]);
+                            const bool gt1 = s > mx[m][g], gt2 = s > sc[m][g];
+                            isc[m][g] = gt1 ? imx[m][g] : (gt2 ? col0 + j : isc[m][g]);
+                            imx[m][g] = gt1 ? col0 + j : imx[m][g];
+                            sc[m][g] = fmaxf(sc[m][g], fminf(mx[m][g], s));
+                            mx[m][g] = fmaxf(mx[m][g], s);
+                        }
                     }
                 }
             }
@@ -389,26 +401,32 @@ match_mma(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         // (a named barrier over the 8 epilogue warps), the lower half's warps merge -- strict >, so equal scores keep
         // the lower index, which is theirs -- and write ONE entry per (split, row, group).
         const int row = quarter * 32 + lane;
-        float4* xc = xchg + mblk * (kBM * 8);
         if (chalf == 1) {
 #pragma unroll
-            for (int g = 0; g < 8; g++) xc[row * 8 + g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
+            for (int m = 0; m < MB; m++)
+#pragma unroll
+                for (int g = 0; g < 8; g++)
+                    xchg[(m * kBM + row) * 8 + g] = make_float4(mx[m][g], sc[m][g], __int_as_float(imx[m][g]), __int_as_float(isc[m][g]));
         }
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + mblk), "n"(kEpiWarps * 32) : "memory");
-        if (chalf == 0 && (rb0 + mblk) * kBM < n1pad) {  // (a CTA's last row block may lie past the rows)
-            Top2* dst = part + ((size_t)split * n1pad + (size_t)(rb0 + mblk) * kBM + row) * 8;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (chalf == 0) {
 #pragma unroll
-            for (int g = 0; g < 8; g++) {
-                const float4 o = xc[row * 8 + g];
-                const float ov[2] = {o.x, o.y};
-                const int oi[2] = {__float_as_int(o.z), __float_as_int(o.w)};
+            for (int m = 0; m < MB; m++) {
+                if ((rb0 + m) * kBM >= n1pad) continue;  // (a CTA's last row block may lie past the rows)
+                Top2* dst = part + ((size_t)split * n1pad + (size_t)(rb0 + m) * kBM + row) * 8;
 #pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    if (oi[q] < 0) continue;
-                    if (ov[q] > mx[g]) { sc[g] = mx[g]; isc[g] = imx[g]; mx[g] = ov[q]; imx[g] = oi[q]; }
-                    else if (ov[q] > sc[g]) { sc[g] = ov[q]; isc[g] = oi[q]; }
+                for (int g = 0; g < 8; g++) {
+                    const float4 o = xchg[(m * kBM + row) * 8 + g];
+                    const float ov[2] = {o.x, o.y};
+                    const int oi[2] = {__float_as_int(o.z), __float_as_int(o.w)};
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        if (oi[q] < 0) continue;
+                        if (ov[q] > mx[m][g]) { sc[m][g] = mx[m][g]; isc[m][g] = imx[m][g]; mx[m][g] = ov[q]; imx[m][g] = oi[q]; }
+                        else if (ov[q] > sc[m][g]) { sc[m][g] = ov[q]; isc[m][g] = oi[q]; }
+                    }
+                    reinterpret_cast<float4*>(dst)[g] = make_float4(mx[m][g], sc[m][g], __int_as_float(imx[m][g]), __int_as_float(isc[m][g]));
                 }
-                reinterpret_cast<float4*>(dst)[g] = make_float4(mx[g], sc[g], __int_as_float(imx[g]), __int_as_float(isc[g]));
             }
         }
     }
