@@ -731,6 +731,48 @@ def test_tma_descriptor_path_equals_gather_path(monkeypatch):
         det1.close()
 
 
+def test_tma_descriptor_path_batch_and_doubled(monkeypatch):
+    """The opt-in TMA descriptor path with several frame slots (the tensor maps index the slot as their third coordinate,
+    the class lists are per slot) and with doubled=true (the lattice lives on the 2x frame): descriptors equal to the
+    default path's, frame by frame."""
+    sb = _sb()
+    torch = _torch()
+    w, h, nb = 400, 300, 3
+    frames = np.stack([sb.synth_frame(w, h, 40 + i) for i in range(nb)])
+    pitch = sb.iAlignUp(w, 128)
+    buf = np.zeros((nb, h, pitch), np.uint8)
+    buf[:, :, :w] = frames
+    d_imgs = torch.from_numpy(buf).cuda()
+    for doubled in (False, True):
+        out = []
+        for tma in (0, 1):
+            if tma:
+                monkeypatch.setenv("SURFB200_DESCRIBE_TMA", "1")
+            det = make_det(w, h, 3, max_pts=8192, batch=nb, doubled=doubled)
+            if tma:
+                monkeypatch.delenv("SURFB200_DESCRIBE_TMA")
+            pts = torch.zeros((nb, 8192 * 48), dtype=torch.uint8, device="cuda")
+            cnt = torch.zeros(nb, dtype=torch.int32, device="cuda")
+            desc = torch.zeros((nb, 8192, 64), dtype=torch.float32, device="cuda")
+            for _ in range(2):
+                det.detect_batch(d_imgs, pitch, pts, cnt, desc)
+            torch.cuda.synchronize()
+            c = cnt.cpu().numpy()
+            res = []
+            for f in range(nb):
+                p = pts[f].cpu().numpy().view(sb.POINT_DTYPE)[: c[f]]
+                d = desc[f, : c[f]].cpu().numpy()
+                o = np.lexsort((p["scale"], p["y"], p["x"]))
+                res.append((p[o], d[o]))
+            out.append(res)
+            det.close()
+        for f in range(nb):
+            (p0, d0), (p1, d1) = out[0][f], out[1][f]
+            assert len(p0) == len(p1) > 50 and np.array_equal(p0["x"], p1["x"])
+            l2 = np.linalg.norm(d0 - d1, axis=1)
+            assert l2.max() <= 1e-5, f"doubled={doubled} frame {f}: L2 max {l2.max():.3e}"
+
+
 def test_match_pairs_equals_match_per_pair():
     """sb_match_pairs_async (all stereo pairs of a detect batch in one launch sequence, counts read on the device) gives,
     per pair, exactly the five match fields of sb_match on the same keypoints and descriptors; a custom pair list, a
