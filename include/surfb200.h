@@ -114,7 +114,11 @@ int sb_match(sb_ctx* ctx, sb_point* d_pts1, sb_point* h_pts1, int n1, const floa
              int n2, const float* d_feat2);
 
 /* The same matching, enqueued on `stream` (used as given) with no host copy and no synchronisation:
- * for pipelines that keep stereo pairs on the device (BASELINE config 5).                       */
+ * for pipelines that keep stereo pairs on the device (BASELINE config 5).
+ * All matching calls of a context share ONE scratch (split operands, partial top-2): issue them on a single stream (or
+ * order the streams yourself). The scratch only grows: a call that needs more than any call before reallocates it
+ * (cudaFree + cudaMalloc: a device-wide synchronisation, not allowed under stream capture) -- run the largest problem once
+ * before capturing a graph.                                                                                          */
 int sb_match_async(sb_ctx* ctx, sb_point* d_pts1, int n1, const float* d_feat1, const sb_point* d_pts2, int n2,
                    const float* d_feat2, void* stream);
 
