@@ -150,6 +150,10 @@ struct DescAux {
     int* cls_idx = nullptr;
     int* cls_cnt = nullptr;
     int slot0 = 0;                // first frame slot of this launch inside the context's buffers
+    // called (if set) right before the last descriptor kernel is launched -- after the orientation pass of the rotated path --
+    // when the keypoints are final: the single-frame call starts their copy to the host there
+    cudaError_t (*before_last)(void*) = nullptr;
+    void* before_last_arg = nullptr;
 };
 cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, sb_point* d_points, long long pts_stride,
                             const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,

@@ -48,6 +48,9 @@ struct sb_ctx {
     cudaStream_t stream = nullptr;
     // ingest / egress streams and per-chunk events of the pipelined host-buffer path (sb_detect_batch_host)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr, stream2 = nullptr;
+    // synchronous single-frame call: count and keypoints go to the host on a side branch while the descriptor kernel runs
+    cudaStream_t s_side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     HostJob job[kHostSets];
     int next_set = 0;
     // scratch, `batch` frame slots each
@@ -228,6 +231,9 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
         for (cudaEvent_t e : J.ev_done) cudaEventDestroy(e);
         for (cudaEvent_t e : J.ev_end) if (e) cudaEventDestroy(e);
     }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -270,6 +276,9 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     // a fill of the result buffers cannot land after the results). The synchronous entry points run here; the *_async
     // ones use the caller's stream as given.
     ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault));
+    ok(cudaStreamCreateWithFlags(&c->s_side, cudaStreamNonBlocking));
+    ok(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     ok(cudaMalloc((void**)&c->d_integral, isz));
     ok(cudaMalloc((void**)&c->d_integral_ph, isz));
     ok(cudaMalloc((void**)&c->d_resp, rsz));
@@ -345,7 +354,7 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
 // The frames use scratch slots [slot0, slot0 + nframes).
 static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
                           sb_point* d_points, int* d_counts, float* d_desc, cudaStream_t st, cudaEvent_t* ev = nullptr,
-                          int slot0 = 0) {
+                          int slot0 = 0, int early_copy_points = -1) {
     const PipeP& P = ctx->P;
     int* integral = ctx->d_integral + (size_t)slot0 * P.istride;
     int* integral_ph = ctx->d_integral_ph + (size_t)slot0 * P.istride;
@@ -371,14 +380,34 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
     CU(launch_clamp_counts(d_counts, nframes, P.max_pts, ctx->d_cand_count + slot0, ctx->d_work + slot0,
                            ctx->d_work + ctx->prm.batch + slot0, ctx->d_cls_cnt ? ctx->d_cls_cnt + 4 * slot0 : nullptr, st));
     if (ev) CU(cudaEventRecord(ev[3], st));
+    // single-frame call: as soon as the keypoints are final (before the last descriptor kernel; the orientation pass of the
+    // rotated path writes `ori` first) the count and the first points leave for the host on a side stream beside that
+    // kernel, and join the main stream again at the end -- inside the captured graph this is a second branch
+    struct Early { sb_ctx* c; cudaStream_t st; int* d_counts; sb_point* d_points; int n; bool done; } early_arg{ctx, st, d_counts, d_points, early_copy_points, false};
+    const bool early = early_copy_points >= 0 && d_desc && ctx->s_side;
     if (d_desc) {
         DescAux aux;
         aux.maps = ctx->d_desc_maps; aux.cls_idx = ctx->d_cls_idx; aux.cls_cnt = ctx->d_cls_cnt; aux.slot0 = slot0;
+        if (early) {
+            aux.before_last_arg = &early_arg;
+            aux.before_last = [](void* a) -> cudaError_t {
+                Early& E = *static_cast<Early*>(a);
+                cudaError_t e = cudaEventRecord(E.c->ev_fork, E.st);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(E.c->s_side, E.c->ev_fork, 0);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(E.c->h_counts, E.d_counts, sizeof(int), cudaMemcpyDeviceToHost, E.c->s_side);
+                if (e == cudaSuccess && E.n > 0)
+                    e = cudaMemcpyAsync(E.c->h_pts, E.d_points, sizeof(sb_point) * (size_t)E.n, cudaMemcpyDeviceToHost, E.c->s_side);
+                if (e == cudaSuccess) e = cudaEventRecord(E.c->ev_join, E.c->s_side);
+                E.done = e == cudaSuccess;
+                return e;
+            };
+        }
         CU(launch_describe(P, nframes, integral, d_points, P.max_pts, d_counts, -1, d_desc,
                            (long long)P.max_pts * P.nfeatures, ctx->sm_count, ctx->d_work + slot0, ctx->d_work + ctx->prm.batch + slot0, aux, st));
     }
+    if (early_arg.done) CU(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     if (ev) CU(cudaEventRecord(ev[4], st));
-    return SB_OK;
+    return early_arg.done ? 1 : SB_OK;  // 1: the count and the points are already on their way
 }
 
 extern "C" int sb_detect_batch_profile(sb_ctx* ctx, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
@@ -457,7 +486,8 @@ extern "C" int sb_detect_and_compute(sb_ctx* ctx, const uint8_t* d_image, int w,
     constexpr int kSpec = 8192;
     const int spec = h_points ? std::min(P.max_pts, kSpec) : 0;
     auto enqueue_all = [&]() -> int {
-        const int rc = enqueue_frames(ctx, d_image, 0, pitch, 1, d_points, ctx->d_counts, d_desc, st);
+        const int rc = enqueue_frames(ctx, d_image, 0, pitch, 1, d_points, ctx->d_counts, d_desc, st, nullptr, 0, spec);
+        if (rc == 1) return SB_OK;  // copied on the side branch, beside the descriptor kernel
         if (rc != SB_OK) return rc;
         CU(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (spec > 0) CU(cudaMemcpyAsync(ctx->h_pts, d_points, sizeof(sb_point) * (size_t)spec, cudaMemcpyDeviceToHost, st));

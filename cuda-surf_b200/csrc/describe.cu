@@ -751,6 +751,7 @@ cudaError_t launch_describe(const PipeP& P, int nframes, const int* d_integral, 
     cudaError_t e = cudaSuccess;
     if (!P.upright) e = launch_dep(orient_kernel, grid, block, 0, st, P, d_integral, d_points, pts_stride, d_counts, fixed_count, d_work_orient);
     if (e != cudaSuccess) return e;
+    if (aux.before_last && (e = aux.before_last(aux.before_last_arg)) != cudaSuccess) return e;
     if (P.upright) {
         const size_t smem = ((size_t)kWarpsPerCta * (P.desc_wsz * P.orient_size + P.desc_wsz) * kTS + kWarpsPerCta * kRowTab * 4 + 40) * sizeof(float);
         if (P.orient_size == 4) {
