@@ -140,11 +140,13 @@ cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t imag
                             int* d_integral, int* d_integral_ph, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);
 cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, const int* d_integral_ph, float* d_resp,
                            cudaStream_t st);
+// d_done: one zeroed unsigned per frame (self re-arming); d_work, d_work_orient, d_cls_cnt: re-armed by the last refine block
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
-                       int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st);
+                       int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, unsigned* d_done, int* d_work,
+                       int* d_work_orient, int* d_cls_cnt /* 4 ints per frame, may be null */, cudaStream_t st);
 // What the TMA descriptor path (describe_tma.cu) needs besides the integral image: the tensor maps over the context's
 // integral buffer, the per-slot keypoint class lists [batch][2][max_pts] and their counters [batch][4] = {keypoints on the
-// TMA path, on the gather path, work counter of either kernel}, zero on entry (clamp_counts_kernel / sb_describe re-arm them).
+// TMA path, on the gather path, work counter of either kernel}, zero on entry (the last nms_refine block / sb_describe re-arm them).
 struct DescAux {
     const void* maps = nullptr;   // device array of CUtensorMap (128 B each); nullptr: gather kernel only
     int* cls_idx = nullptr;
@@ -163,8 +165,6 @@ bool describe_tma_applies(const PipeP& P);
 cudaError_t launch_describe_tma(const PipeP& P, int nframes, const DescAux& aux, sb_point* d_points, long long pts_stride,
                                 const int* d_counts, int fixed_count, float* d_desc, long long desc_stride, int sm_count,
                                 cudaStream_t st);
-cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, int* d_work_orient,
-                                int* d_cls_cnt /* 4 ints per frame, may be null */, cudaStream_t st);
 // grow-only device scratch of the matcher (split-bf16 operands, per-split group top-2), owned by the context
 struct MatchScratch {
     void* a = nullptr; void* b = nullptr; void* part = nullptr;

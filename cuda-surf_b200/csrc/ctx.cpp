@@ -61,7 +61,8 @@ struct sb_ctx {
     int* d_counts = nullptr;
     unsigned* d_cand = nullptr;   // NMS candidate queues, `batch` slots of cand_cap packed words
     int* d_cand_count = nullptr;
-    int* d_work = nullptr;        // per-slot work counter of the descriptor kernel (zeroed by clamp_counts)
+    int* d_work = nullptr;        // per-slot work counters of the descriptor kernels (re-armed by the last nms_refine block)
+    unsigned* d_refine_done = nullptr;  // per-slot count of finished nms_refine blocks (wraps to zero by itself)
     int cand_cap = 0;
     // TMA descriptor path (describe_tma.cu): tensor maps over d_integral, keypoint class lists and their counters
     void* d_desc_maps = nullptr;
@@ -71,7 +72,7 @@ struct sb_ctx {
     int up_pitch = 0;
     int* h_counts = nullptr;          // pinned
     sb_point* h_pts = nullptr;        // pinned, max_pts
-    // sb_detect_and_compute replays one captured CUDA graph per (image, points, descriptor) pointer set: the eight launches,
+    // sb_detect_and_compute replays one captured CUDA graph per (image, points, descriptor) pointer set: the seven launches,
     // the counter memset and the two result copies of a frame go down as one submission
     struct FrameGraph { const void* img; int pitch; void* pts; void* desc; int spec; cudaGraphExec_t exec; unsigned long long used; };
     std::vector<FrameGraph> graphs;
@@ -217,7 +218,7 @@ extern "C" void sb_destroy(sb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_integral); cudaFree(ctx->d_integral_ph); cudaFree(ctx->d_resp); cudaFree(ctx->d_colsum); cudaFree(ctx->d_rowsum);
-    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_work); cudaFree(ctx->d_desc_own);
+    cudaFree(ctx->d_tilesum); cudaFree(ctx->d_counts); cudaFree(ctx->d_up); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_work); cudaFree(ctx->d_refine_done); cudaFree(ctx->d_desc_own);
     cudaFree(ctx->d_desc_maps); cudaFree(ctx->d_cls_idx); cudaFree(ctx->d_cls_cnt);
     for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
     free_match_scratch(ctx->match_ws);
@@ -293,6 +294,7 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
     ok(cudaMalloc((void**)&c->d_cand, sizeof(unsigned) * (size_t)c->cand_cap * B));
     ok(cudaMalloc((void**)&c->d_cand_count, sizeof(int) * B));
     ok(cudaMalloc((void**)&c->d_work, sizeof(int) * 2 * B));  // [0, B): descriptor pass, [B, 2B): orientation pass
+    ok(cudaMalloc((void**)&c->d_refine_done, sizeof(unsigned) * B));
     // opt-in (environment, read at context creation): the TMA-staged descriptor kernel for step-2 keypoints. Measured
     // on the B200 it is as fast as the gather kernel on those keypoints, not faster, so the default stays off.
     const char* tma_env = getenv("SURFB200_DESCRIBE_TMA");
@@ -317,6 +319,7 @@ extern "C" int sb_create(sb_ctx** out, const sb_params* params) {
         ok(cudaMemsetAsync(c->d_counts, 0, sizeof(int) * B, c->stream));
         ok(cudaMemsetAsync(c->d_cand_count, 0, sizeof(int) * B, c->stream));
         ok(cudaMemsetAsync(c->d_work, 0, sizeof(int) * 2 * B, c->stream));
+        ok(cudaMemsetAsync(c->d_refine_done, 0, sizeof(unsigned) * B, c->stream));
         ok(cudaStreamSynchronize(c->stream));
     }
     if (e != cudaSuccess) {
@@ -344,7 +347,7 @@ extern "C" int sb_get_info(const sb_ctx* ctx, sb_info* info) {
     const bool fast0 = (P.sampling == 2 || P.sampling == 4) && P.init_lobe == 3 && P.max_scale == 5;
     const int nhess = fast0 ? (P.noctaves > 1 ? 2 : 1) : 1;
     info->cand_capacity = ctx->cand_cap;
-    info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + nhess + 2 /*nms scan, refine*/ + 1 /*clamp*/ + (P.upright ? 1 : 2) +
+    info->kernels_per_frame = (P.doubled ? 1 : 0) + 2 /*integral*/ + nhess + 2 /*nms scan, refine (which also closes the frame's counters)*/ + (P.upright ? 1 : 2) +
                               (ctx->d_desc_maps ? 2 : 0) /*classify + TMA descriptor kernel*/;
     return SB_OK;
 }
@@ -376,9 +379,8 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
     CU(launch_hessian(P, nframes, integral, integral_ph, resp, st));
     if (ev) CU(cudaEventRecord(ev[2], st));
     CU(launch_nms(P, nframes, integral, resp, d_points, d_counts, ctx->d_cand + (size_t)slot0 * ctx->cand_cap,
-                  ctx->d_cand_count + slot0, ctx->cand_cap, st));
-    CU(launch_clamp_counts(d_counts, nframes, P.max_pts, ctx->d_cand_count + slot0, ctx->d_work + slot0,
-                           ctx->d_work + ctx->prm.batch + slot0, ctx->d_cls_cnt ? ctx->d_cls_cnt + 4 * slot0 : nullptr, st));
+                  ctx->d_cand_count + slot0, ctx->cand_cap, ctx->d_refine_done + slot0, ctx->d_work + slot0,
+                  ctx->d_work + ctx->prm.batch + slot0, ctx->d_cls_cnt ? ctx->d_cls_cnt + 4 * slot0 : nullptr, st));
     if (ev) CU(cudaEventRecord(ev[3], st));
     // single-frame call: as soon as the keypoints are final (before the last descriptor kernel; the orientation pass of the
     // rotated path writes `ori` first) the count and the first points leave for the host on a side stream beside that

@@ -338,8 +338,8 @@ nms_scan_tile_kernel(const __grid_constant__ PipeP P, const float* __restrict__ 
 // grid (ctas, nframes), 128 threads, grid-stride over the frame's candidates.
 __global__ void __launch_bounds__(128)
 nms_refine_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, const float* __restrict__ Rbase,
-                  const unsigned* __restrict__ cand, const int* __restrict__ cand_count, int cand_cap,
-                  sb_point* __restrict__ points, int* __restrict__ counts) {
+                  const unsigned* __restrict__ cand, int* cand_count, int cand_cap,
+                  sb_point* __restrict__ points, int* counts, unsigned* __restrict__ done, int* work, int* work2, int* cls_cnt) {
     pdl_wait();
     const int f = blockIdx.y, lane = threadIdx.x & 31;
     const int ncand = min(cand_count[f], cand_cap);
@@ -414,21 +414,26 @@ nms_refine_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase
             }
         }
     }
-}
-
-// Clamp the keypoint counts to the capacity and re-arm the candidate counters for the next call (they are zero after
-// sb_create, and every pass leaves them zero again: no memset in the per-frame sequence).
-__global__ void clamp_counts_kernel(int* counts, int n, int max_pts, int* cand_count, int* work, int* work2, int* cls_cnt) {
-    pdl_wait();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        counts[i] = min(counts[i], max_pts); cand_count[i] = 0; work[i] = 0; work2[i] = 0;
-        if (cls_cnt) *reinterpret_cast<int4*>(cls_cnt + 4 * i) = make_int4(0, 0, 0, 0);
+    // The block that finishes a frame's refinement last closes the frame: the keypoint count is clamped to the capacity and the
+    // candidate counter and the work counters of the descriptor kernels are re-armed for the next call (they are zero after
+    // sb_create, and every pass leaves them zero again: no memset and no extra launch in the per-frame sequence). atomicInc
+    // wraps at gridDim.x - 1, so `done` re-arms itself.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicInc(done + f, gridDim.x - 1) == gridDim.x - 1) {
+            __threadfence();
+            const int c = *reinterpret_cast<volatile int*>(counts + f);
+            counts[f] = min(c, P.max_pts);
+            cand_count[f] = 0; work[f] = 0; work2[f] = 0;
+            if (cls_cnt) *reinterpret_cast<int4*>(cls_cnt + 4 * f) = make_int4(0, 0, 0, 0);
+        }
     }
 }
 
 cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const float* d_resp, sb_point* d_points,
-                       int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, cudaStream_t st) {
+                       int* d_counts, unsigned* d_cand, int* d_cand_count, int cand_cap, unsigned* d_done, int* d_work,
+                       int* d_work_orient, int* d_cls_cnt, cudaStream_t st) {
     // standard octaves (5 layers, the two cell lattices at most 2 samples apart): shared-memory scan, one CTA per tile
     cudaError_t e = cudaSuccess;
     bool tiled = P.max_scale == 5;
@@ -444,12 +449,8 @@ cudaError_t launch_nms(const PipeP& P, int nframes, const int* d_integral, const
         e = launch_dep(nms_scan_kernel, dim3(P.nms_tiles, nframes), dim3(32, 8), 0, st, P, d_resp, d_cand, d_cand_count, cand_cap);
     // ~5 k candidates per 1080p frame: 48 CTAs of 128 threads cover them in one pass, more are looped over
     if (e != cudaSuccess) return e;
-    return launch_dep(nms_refine_kernel, dim3(48, nframes), dim3(128), 0, st, P, d_integral, d_resp, d_cand, d_cand_count, cand_cap, d_points, d_counts);
-}
-
-cudaError_t launch_clamp_counts(int* d_counts, int nframes, int max_pts, int* d_cand_count, int* d_work, int* d_work_orient,
-                                int* d_cls_cnt, cudaStream_t st) {
-    return launch_dep(clamp_counts_kernel, dim3((nframes + 255) / 256), dim3(256), 0, st, d_counts, nframes, max_pts, d_cand_count, d_work, d_work_orient, d_cls_cnt);
+    return launch_dep(nms_refine_kernel, dim3(48, nframes), dim3(128), 0, st, P, d_integral, d_resp, d_cand, d_cand_count, cand_cap, d_points, d_counts,
+                      d_done, d_work, d_work_orient, d_cls_cnt);
 }
 
 }  // namespace sb
