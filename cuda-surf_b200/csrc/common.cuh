@@ -137,7 +137,8 @@ inline cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_pitch, int w, int h, uint8_t* d_dst,
                               size_t dst_stride, int dst_pitch, int nframes, cudaStream_t st);
 cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
-                            int* d_integral, int* d_integral_ph, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st);
+                            int* d_integral, int* d_integral_ph, int* d_colsum, int* d_rowsum, int* d_tilesum,
+                            int* d_counts /* one per frame, zeroed by the first kernel; may be null */, cudaStream_t st);
 cudaError_t launch_hessian(const PipeP& P, int nframes, const int* d_integral, const int* d_integral_ph, float* d_resp,
                            cudaStream_t st);
 // d_done: one zeroed unsigned per frame (self re-arming); d_work, d_work_orient, d_cls_cnt: re-armed by the last refine block

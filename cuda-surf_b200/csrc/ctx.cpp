@@ -365,7 +365,6 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
     int* colsum = ctx->d_colsum + (size_t)slot0 * P.nbands * P.nchunks * 256;
     int* rowsum = ctx->d_rowsum + (size_t)slot0 * P.nbands * 32 * P.nchunks;
     int* tilesum = ctx->d_tilesum + (size_t)slot0 * P.nbands * P.nchunks;
-    CU(cudaMemsetAsync(d_counts, 0, sizeof(int) * nframes, st));
     if (ev) CU(cudaEventRecord(ev[0], st));
     if (P.doubled) {
         // the 2x frame replaces the caller's as the input of the integral stage
@@ -374,7 +373,7 @@ static int enqueue_frames(sb_ctx* ctx, const uint8_t* d_images, size_t image_str
         CU(launch_upsample2x(d_images, image_stride, pitch, ctx->prm.width, ctx->prm.height, up, ustride, ctx->up_pitch, nframes, st));
         d_images = up; image_stride = ustride; pitch = ctx->up_pitch;
     }
-    CU(launch_integral(P, d_images, image_stride, pitch, nframes, integral, integral_ph, colsum, rowsum, tilesum, st));
+    CU(launch_integral(P, d_images, image_stride, pitch, nframes, integral, integral_ph, colsum, rowsum, tilesum, d_counts, st));
     if (ev) CU(cudaEventRecord(ev[1], st));
     CU(launch_hessian(P, nframes, integral, integral_ph, resp, st));
     if (ev) CU(cudaEventRecord(ev[2], st));

@@ -68,7 +68,9 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 template <bool ALIGNED>
 __global__ void __launch_bounds__(kThreads)
 integral_reduce(const __grid_constant__ PipeP P, const uint8_t* __restrict__ imgs, size_t image_stride, int pitch,
-                int* __restrict__ T, int* __restrict__ R, int* __restrict__ TT) {
+                int* __restrict__ T, int* __restrict__ R, int* __restrict__ TT, int* __restrict__ counts) {
+    // the first kernel of a frame also zeroes the frame's keypoint counter (it was a memset node in front of every frame)
+    if (counts && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) counts[blockIdx.z] = 0;
     __shared__ int part[8][kChunk];
     __shared__ int wtot[8];
     const int c = blockIdx.x, b = blockIdx.y, f = blockIdx.z;
@@ -295,14 +297,15 @@ cudaError_t launch_upsample2x(const uint8_t* d_src, size_t src_stride, int src_p
 }
 
 cudaError_t launch_integral(const PipeP& P, const uint8_t* d_images, size_t image_stride, int pitch, int nframes,
-                            int* d_integral, int* d_integral_ph, int* d_colsum, int* d_rowsum, int* d_tilesum, cudaStream_t st) {
+                            int* d_integral, int* d_integral_ph, int* d_colsum, int* d_rowsum, int* d_tilesum, int* d_counts,
+                            cudaStream_t st) {
     const dim3 grid(P.nchunks, P.nbands, nframes), block(kThreads);
     const bool aligned = (pitch % 8 == 0) && (image_stride % 8 == 0) && ((uintptr_t)d_images % 8 == 0);
     if (aligned) {
-        integral_reduce<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
+        integral_reduce<true><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_counts);
         return launch_dep(integral_scan<true>, grid, block, 0, st, P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
     } else {
-        integral_reduce<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum);
+        integral_reduce<false><<<grid, block, 0, st>>>(P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_counts);
         return launch_dep(integral_scan<false>, grid, block, 0, st, P, d_images, image_stride, pitch, d_colsum, d_rowsum, d_tilesum, d_integral, d_integral_ph);
     }
     return cudaGetLastError();
