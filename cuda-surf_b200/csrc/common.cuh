@@ -77,6 +77,24 @@ __device__ __forceinline__ int haar_x(const int* __restrict__ I, int ip, int x, 
     return box_sum(I, ip, x, x + s, y - s, y + s) - box_sum(I, ip, x - s, x, y - s, y + s);
 }
 
+// Both Haar responses of the (2s+1)^2 window at (x, y) from the 12 distinct corners the two box pairs share (haar_x and
+// haar_y above read 16), with ONE 32-bit element index per row and 64-bit row pointers made opaque: written through
+// box_sum the compiler spent ~70 instructions of 64-bit carry chains on the 16 addresses of a sample (ncu source view of the
+// rotated descriptor kernel, round 2). Integer arithmetic, so the values are those of haar_x / haar_y exactly.
+__device__ __forceinline__ void haar_xy(const int* __restrict__ I, int ip, int x, int y, int s, int& hx, int& hy) {
+    const int base = y * ip + x, sip = s * ip;
+    const int* pm = I + (base - sip);       // row y - s
+    const int* pz = I + base;               // row y (row y + 1 is ip further)
+    const int* pq = I + (base + sip + ip);  // row y + s + 1
+    asm volatile("" : "+l"(pm), "+l"(pz), "+l"(pq));
+    // columns A = x - s, B = x, C = x + 1, D = x + s + 1
+    const int mA = __ldg(pm - s), mB = __ldg(pm), mC = __ldg(pm + 1), mD = __ldg(pm + s + 1);
+    const int qA = __ldg(pq - s), qB = __ldg(pq), qC = __ldg(pq + 1), qD = __ldg(pq + s + 1);
+    const int zA = __ldg(pz - s), zD = __ldg(pz + s + 1), uA = __ldg(pz + (ip - s)), uD = __ldg(pz + (ip + s + 1));
+    hx = (qD + mB - mD - qB) - (qC + mA - mC - qA);
+    hy = (zD - zA) + (uD - uA) - (mD - mA) - (qD - qA);
+}
+
 // The geometry of one keypoint's sampling lattice (surfd.cu:1578-1590), shared by both descriptor kernels.
 struct KpGeom {
     float fx, fy, spacing;

@@ -105,8 +105,10 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
             float angle = 0.f, psum = 0.f;
             const int distsq = y1 * y1 + x1 * x1;
             if (yy + hs + 2 < P.ih && yy - hs > -1 && xx + hs + 2 < P.iw && xx - hs > -1) {
-                const float dx = __fmul_rn(__int2float_rn(haar_x(I, P.ip, xx, yy, hs)), kR255);
-                const float dy = __fmul_rn(__int2float_rn(haar_y(I, P.ip, xx, yy, hs)), kR255);
+                int hx, hy;
+                haar_xy(I, P.ip, xx, yy, hs, hx, hy);
+                const float dx = __fmul_rn(__int2float_rn(hx), kR255);
+                const float dy = __fmul_rn(__int2float_rn(hy), kR255);
                 const float mag = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
                 if (mag > 0.f) {
                     angle = fast_atan2(dy, dx);
@@ -249,28 +251,33 @@ orient_kernel(const __grid_constant__ PipeP P, const int* __restrict__ Ibase, sb
 // descriptor copy h[element*32 + lane]. Branch-free: a cell outside the WxW grid gets weight 0 and is redirected to a
 // per-lane dummy word (row `dummy` of h), so the 8 addresses never alias a live one and the 8 loads are issued together
 // before the 8 stores (with a branch per quadrant the updates were 8 dependent shared-memory round trips).
-__device__ __forceinline__ void place(float* __restrict__ h, int lane, int W, int O, int dummy, float mag1, int ori1, float mag2,
-                                      int ori2, float rx, float cx) {
+// hs = shared-memory address of this lane's column of the private copy (h + lane), row stride 128 bytes: every update is
+// one 32-bit address (cell * O + bin) * 128 + hs -- as generic pointers the eight addresses cost two LEA each on top of the
+// index arithmetic.
+__device__ __forceinline__ void place(uint32_t hs, int W, int O, int dummy, float mag1, int ori1, float mag2, int ori2, float rx,
+                                      float cx) {
     const int ri = __float2int_rz(rx >= 0.f ? rx : __fsub_rn(rx, 1.f));
     const int ci = __float2int_rz(cx >= 0.f ? cx : __fsub_rn(cx, 1.f));
     const float rfrac = __fsub_rn(rx, __int2float_rn(ri));
     const float cfrac = __fsub_rn(cx, __int2float_rn(ci));
     const bool r0ok = ri >= 0, r1ok = ri + 1 < W, c0ok = ci >= 0, c1ok = ci + 1 < W;
     const float rw0 = __fsub_rn(1.f, rfrac), rw1 = rfrac, cw0 = __fsub_rn(1.f, cfrac), cw1 = cfrac;
-    const int e00 = (r0ok && c0ok) ? (ri * W + ci) * O : dummy;
-    const int e01 = (r0ok && c1ok) ? (ri * W + ci + 1) * O : dummy;
-    const int e10 = (r1ok && c0ok) ? ((ri + 1) * W + ci) * O : dummy;
-    const int e11 = (r1ok && c1ok) ? ((ri + 1) * W + ci + 1) * O : dummy;
-    float* p[8] = {h + (e00 + ori1) * 32 + lane, h + (e00 + ori2) * 32 + lane, h + (e01 + ori1) * 32 + lane, h + (e01 + ori2) * 32 + lane,
-                   h + (e10 + ori1) * 32 + lane, h + (e10 + ori2) * 32 + lane, h + (e11 + ori1) * 32 + lane, h + (e11 + ori2) * 32 + lane};
-    const float a0 = __fmul_rn(mag1, rw0), b0 = __fmul_rn(mag2, rw0), a1 = __fmul_rn(mag1, rw1), b1 = __fmul_rn(mag2, rw1);
+    const int e00i = (ri * W + ci) * O;  // element index of cell (ri, ci), bin 0
+    const int e00 = (r0ok && c0ok) ? e00i : dummy;
+    const int e01 = (r0ok && c1ok) ? e00i + O : dummy;
+    const int e10 = (r1ok && c0ok) ? e00i + W * O : dummy;
+    const int e11 = (r1ok && c1ok) ? e00i + W * O + O : dummy;
+    const uint32_t a1 = hs + 128u * (uint32_t)ori1, a2 = hs + 128u * (uint32_t)ori2;
+    const uint32_t p[8] = {a1 + 128u * e00, a2 + 128u * e00, a1 + 128u * e01, a2 + 128u * e01,
+                           a1 + 128u * e10, a2 + 128u * e10, a1 + 128u * e11, a2 + 128u * e11};
+    const float a0 = __fmul_rn(mag1, rw0), b0 = __fmul_rn(mag2, rw0), a1f = __fmul_rn(mag1, rw1), b1 = __fmul_rn(mag2, rw1);
     const float add[8] = {__fmul_rn(a0, cw0), __fmul_rn(b0, cw0), __fmul_rn(a0, cw1), __fmul_rn(b0, cw1),
-                          __fmul_rn(a1, cw0), __fmul_rn(b1, cw0), __fmul_rn(a1, cw1), __fmul_rn(b1, cw1)};
+                          __fmul_rn(a1f, cw0), __fmul_rn(b1, cw0), __fmul_rn(a1f, cw1), __fmul_rn(b1, cw1)};
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = *p[k];
+    for (int k = 0; k < 8; k++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(p[k]));
 #pragma unroll
-    for (int k = 0; k < 8; k++) *p[k] = __fadd_rn(v[k], add[k]);
+    for (int k = 0; k < 8; k++) asm volatile("st.shared.f32 [%0], %1;" ::"r"(p[k]), "f"(__fadd_rn(v[k], add[k])) : "memory");
 }
 
 // Rotated descriptor (describeApproxWithoutNormalization + addSample, surfd.cu:2391-2444, 1984-2015): the sampling lattice
@@ -295,6 +302,7 @@ describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__
     for (int t = threadIdx.x; t < 40; t += blockDim.x) s_lut2[t] = P.lut2[t];
     __syncthreads();
     float* h = hbase + warp * hrows * 32;
+    const uint32_t hs = (uint32_t)__cvta_generic_to_shared(h + lane);
     const int n = fixed_count >= 0 ? fixed_count : min(counts[f], P.max_pts);
     const int* I = Ibase + (size_t)f * P.istride + P.ip;
     const sb_point* pts = points + (size_t)f * pts_stride;
@@ -394,15 +402,17 @@ describe_rotated_kernel(const __grid_constant__ PipeP P, const int* __restrict__
                     if (rx > -1.f && rx < fW && cx > -1.f && cx < fW && r >= 1 + S && r < P.ih - 1 - S && c >= 1 + S &&
                         c < P.iw - 1 - S) {
                         const float weight = s_lut2[__float2int_rz(__fmaf_rn(rpos, rpos, __fmul_rn(cpos, cpos)))];
-                        const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_x(I, P.ip, c, r, S))), kR255);
-                        const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(haar_y(I, P.ip, c, r, S))), kR255);
+                        int hx, hy;
+                        haar_xy(I, P.ip, c, r, S, hx, hy);
+                        const float a = __fmul_rn(__fmul_rn(weight, __int2float_rn(hx)), kR255);
+                        const float b = __fmul_rn(__fmul_rn(weight, __int2float_rn(hy)), kR255);
                         const float dx = __fmaf_rn(cose, a, __fmul_rn(sine, b));
                         const float dy = __fmaf_rn(sine, a, -__fmul_rn(cose, b));
                         if (O == 4) {
-                            place(h, lane, W, O, NF, dx, (dx < 0.f ? 0 : 1), dy, (dy < 0.f ? 2 : 3), rx, cx);
+                            place(hs, W, O, NF, dx, (dx < 0.f ? 0 : 1), dy, (dy < 0.f ? 2 : 3), rx, cx);
                         } else {
-                            place(h, lane, W, O, NF, dx, (dy < 0.f ? 0 : 1), fabsf(dx), (dy < 0.f ? 2 : 3), rx, cx);
-                            place(h, lane, W, O, NF, dy, (dx < 0.f ? 4 : 5), fabsf(dy), (dx < 0.f ? 6 : 7), rx, cx);
+                            place(hs, W, O, NF, dx, (dy < 0.f ? 0 : 1), fabsf(dx), (dy < 0.f ? 2 : 3), rx, cx);
+                            place(hs, W, O, NF, dy, (dx < 0.f ? 4 : 5), fabsf(dy), (dx < 0.f ? 6 : 7), rx, cx);
                         }
                     }
                 }
